@@ -1,0 +1,69 @@
+"""EPL-B200: a Blackwell-native hybrid-parallel training framework with the
+capabilities of alibaba/EasyParallelLibrary.
+
+Public surface (reference ``epl/__init__.py:23-55``)::
+
+    import easyparallellibrary_b200 as epl
+    epl.init(epl.Config({"pipeline.num_micro_batch": 4}))
+    with epl.replicate(device_count=1):
+        model = Net()
+    trainer = epl.Trainer(model, optimizer="adamw", lr=1e-4, loss_fn=loss_fn)
+    out = trainer.step(inputs, labels)
+"""
+from __future__ import annotations
+
+from easyparallellibrary_b200.utils.version import VERSION
+from easyparallellibrary_b200.config import Config
+from easyparallellibrary_b200.env import Env
+from easyparallellibrary_b200.cluster import Cluster, VirtualDevice, Device
+from easyparallellibrary_b200.ir.graph import (Graph, GraphKeys, add_to_collection, get_collection,
+                                               get_all_collections)
+from easyparallellibrary_b200.ir.phase import ModelPhase
+from easyparallellibrary_b200.strategies import replicate, split, Replicate, Split
+
+__version__ = VERSION
+
+
+def init(config=None, init_process_group: bool = True):
+  """Reset all state, install the capture hooks, discover the cluster.
+
+  Parity: ``epl.init`` (reference ``epl/__init__.py:38-50``): ``Env.reset`` +
+  ``Env.init(config)`` and a ``Cluster`` — with layout ``"all"`` when
+  ``cluster.colocate_split_and_replicate`` is set, otherwise lazily laid out
+  once the taskgraphs are known.  In addition, under a launcher
+  (``RANK``/``WORLD_SIZE`` present) the ``torch.distributed`` process group is
+  created here: NCCL when this rank has a GPU, gloo otherwise.
+  """
+  import os
+  env = Env.get()
+  env.reset()
+  env.init(config)
+  if init_process_group and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    from easyparallellibrary_b200.runtime.dist import ensure_process_group
+    ensure_process_group()
+  cfg = env.config
+  layout = "all" if cfg.cluster.colocate_split_and_replicate else None
+  env.cluster = Cluster(layout=layout, prefer_intra_node=cfg.cluster.device_place_prefer_intra_node)
+  return env
+
+
+def set_default_strategy(strategy):
+  """Everything created outside an explicit scope belongs to ``strategy``
+  (replicate only).  Calling it again opens the next taskgraph — the idiom the
+  reference's BERT example uses to cut pipeline stages
+  (``examples/bert/modeling.py:829-834``)."""
+  Graph.get().set_default_strategy(strategy)
+
+
+def __getattr__(name):
+  # heavy sub-systems are imported lazily so `import easyparallellibrary_b200` stays cheap
+  if name in ("Trainer", "Engine"):
+    from easyparallellibrary_b200.parallel.engine import Trainer
+    return Trainer
+  if name == "prepare":
+    from easyparallellibrary_b200.parallel.engine import prepare
+    return prepare
+  if name in ("ops", "models", "runtime", "profiler", "communicators", "parallel", "utils"):
+    import importlib
+    return importlib.import_module("easyparallellibrary_b200." + name)
+  raise AttributeError("module 'easyparallellibrary_b200' has no attribute %r" % name)

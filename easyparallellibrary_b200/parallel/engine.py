@@ -1,0 +1,570 @@
+"""The training engine: turns an annotated model into a running hybrid-parallel job.
+
+This is the eager counterpart of the reference's ``Parallel.do_parallelism``
+pipeline (``epl/parallel/parallel.py:211-231``: offload -> micro-batch clone ->
+replica clone -> gradient aggregation -> schedule -> IO slicing -> output
+merging).  Nothing is cloned: replicas are other ranks, micro-batches are loop
+iterations, schedules are instruction lists, gradient aggregation is a set of
+flat buckets reduced over NVLink while backward is still running.
+
+Semantics kept from the reference:
+
+* the batch handed to :meth:`Trainer.step` is split into
+  ``pipeline.num_micro_batch`` micro-batches; with one stage that is gradient
+  accumulation (``runtime/gradient_accumulation.py:40-50``), with several it is
+  the pipeline;
+* gradients: sum over micro-batches (/M if ``mean``) -> reduce over replicas
+  (/N if ``mean``) -> clip -> apply (``graph_editor.py:610-725``);
+  ``communication.clip_after_allreduce`` picks clip-then-reduce vs
+  reduce-then-clip (``hooks.py:173-179``);
+* weights are broadcast from the first replica once (``hooks.py:330-357``);
+* ``GraphKeys`` collections are merged over micro-batches and replicas and
+  returned to the caller (``parallel.py:233-353``);
+* ZeRO ``v0`` shards optimizer state, ``v1`` additionally shards gradients
+  (``runtime/zero.py:88-175``) — here as equal flat shards per bucket instead of
+  variable-granular ownership, which is what makes reduce-scatter (and the fused
+  NVLink kernel) applicable; grouped apply (``optimizer.num_apply_group``)
+  bounds optimizer temporaries (``optimizer_helper.py:75-128``).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from easyparallellibrary_b200.communicators.collective_communicator import CollectiveCommunicator
+from easyparallellibrary_b200.env import Env
+from easyparallellibrary_b200.ir.graph import Graph, GraphKeys
+from easyparallellibrary_b200.ir.phase import ModelPhase, phase_scope
+from easyparallellibrary_b200.parallel.flat import Bucket, FlatParameters
+from easyparallellibrary_b200.parallel.plan import ParallelPlan, build_plan
+from easyparallellibrary_b200.runtime import amp as amp_lib
+from easyparallellibrary_b200.runtime.optimizer import FlatOptimizer, make_hyper
+from easyparallellibrary_b200.utils import constant
+from easyparallellibrary_b200.utils.logging import get_logger
+
+
+@dataclass
+class StepOutput:
+  loss: Optional[torch.Tensor] = None
+  collections: "OrderedDict[str, List[Any]]" = field(default_factory=OrderedDict)
+  skipped: bool = False
+  grad_norm: Optional[torch.Tensor] = None
+  loss_scale: float = 1.0
+
+  def item(self) -> float:
+    return float(self.loss) if self.loss is not None else float("nan")
+
+
+def default_no_decay(p: nn.Parameter) -> bool:
+  return p.dim() <= 1 or getattr(p, "epl_no_decay", False)
+
+
+def _split_batch(batch: Sequence[Any], m: int) -> List[Tuple[Any, ...]]:
+  if m == 1:
+    return [tuple(batch)]
+  cols = []
+  for x in batch:
+    if isinstance(x, torch.Tensor) and x.dim() > 0:
+      if x.shape[0] % m:
+        raise ValueError("batch dimension %d is not divisible by pipeline.num_micro_batch=%d" % (x.shape[0], m))
+      cols.append(x.chunk(m, 0))
+    else:
+      cols.append([x] * m)
+  return [tuple(c[i] for c in cols) for i in range(m)]
+
+
+def sequential_layers(model: nn.Module) -> Optional[List[nn.Module]]:
+  fn = getattr(model, "epl_sequential", None)
+  if callable(fn):
+    return list(fn())
+  if isinstance(model, nn.Sequential):
+    return list(model)
+  return None
+
+
+class Trainer(object):
+  """``Trainer(model, optimizer="adamw", lr=..., loss_fn=...)`` then ``trainer.step(*batch)``.
+
+  ``loss_fn(output, *batch[1:])`` is applied to the model output; without a
+  ``loss_fn`` the model itself must return the loss (``model(*batch)``).
+  """
+
+  def __init__(self, model: nn.Module, optimizer: str = "adamw", loss_fn: Optional[Callable] = None,
+               device: Optional[torch.device] = None, max_grad_norm: Optional[float] = None,
+               no_decay: Callable[[nn.Parameter], bool] = default_no_decay, example_inputs: Optional[Sequence[Any]] = None,
+               baseline: bool = False, **opt_kwargs):
+    env = Env.get()
+    if not env.is_initialized:
+      env.init(None)
+    self.env = env
+    self.config = env.config
+    self.model = model
+    self.loss_fn = loss_fn
+    self.opt_kind = optimizer.lower()
+    self.hyper = make_hyper(self.opt_kind, **opt_kwargs)
+    self.max_grad_norm = max_grad_norm
+    self.no_decay = no_decay
+    self.example_inputs = example_inputs
+    self.baseline = baseline            # reference-equivalent library path (all-reduce + unfused optimizer)
+    self._device = device
+    self._built = False
+    self.global_step = 0
+    self.scaler = amp_lib.make_scaler(self.config.amp.level, self.config.amp.loss_scale)
+    self.hooks: List[Any] = []          # profiler hooks: before_step(trainer) / after_step(trainer, out)
+    self.launch_count = 0
+
+  # ================================================================== build
+  def build(self) -> "Trainer":
+    if self._built:
+      return self
+    from easyparallellibrary_b200.runtime.dist import local_device
+    cfg, env = self.config, self.env
+    graph = Graph.get()
+    self.device = self._device or local_device()
+    if cfg.auto.auto_parallel and cfg.pipeline.num_stages > 1:
+      self._auto_stages(graph)
+    self.plan: ParallelPlan = build_plan(graph, env.cluster, cfg)
+    env.parallel_information[constant.STAGE_POLICY_HEURISTIC] = self.plan.describe()
+    get_logger().info(self.plan.describe())
+
+    # ---- which modules run here ------------------------------------------------------
+    self.stage_modules: Dict[int, nn.Module] = {}
+    layers = sequential_layers(self.model)
+    if self.plan.num_stages > 1:
+      if layers is None:
+        raise RuntimeError("several replicate taskgraphs need a sequential model: an nn.Sequential or a model "
+                           "with epl_sequential() returning its layers in call order")
+      assign = self._assign_layers(layers, graph)
+      for s in range(self.plan.num_stages):
+        mods = [l for l, a in zip(layers, assign) if a == s]
+        self.stage_modules[s] = nn.Sequential(*mods)
+    else:
+      self.stage_modules[0] = self.model
+    local = [self.stage_modules[s] for s in self.plan.local_stages]
+
+    # ---- precision, placement, recompute ---------------------------------------------
+    self.compute_dtype = amp_lib.compute_dtype(cfg.amp.level)
+    for m in local:
+      if self.compute_dtype is not None:
+        amp_lib.cast_module(m, self.compute_dtype, cfg.amp.debug_log)
+      _materialize(m, self.device)
+    if cfg.gradient_checkpoint.type:
+      from easyparallellibrary_b200.runtime.gradient_checkpoint import apply_gradient_checkpoint
+      for m in local:
+        wrapped = apply_gradient_checkpoint(m, cfg.gradient_checkpoint.type, None,
+                                            graph.get_collection(GraphKeys.GC_CHECKPOINTS),
+                                            cfg.gradient_checkpoint.end_taskgraph)
+        get_logger().info("gradient checkpoint: %d segment(s)", len(wrapped))
+
+    # ---- data-parallel groups, flat storage, optimizer ---------------------------------
+    self.dp_comms: Dict[int, CollectiveCommunicator] = {}
+    self.flats: Dict[int, FlatParameters] = {}
+    self.optimizers: Dict[int, List[FlatOptimizer]] = {}
+    zero = cfg.zero.level
+    for s in self.plan.local_stages:
+      tg_index = self.plan.stage_taskgraphs[s]
+      pl = self.plan.placements[tg_index]
+      comm = CollectiveCommunicator("DATA_PARALLEL_GRADS_REDUCE_%d" % s, pl.dp_ranks, device=self.device)
+      self.dp_comms[s] = comm
+      seen, params = set(), []
+      for p in self.stage_modules[s].parameters():
+        if id(p) not in seen and p.requires_grad and not getattr(p, "epl_tp_sharded_grad_skip", False):
+          seen.add(id(p))
+          params.append(p)
+      self.sharded = (zero in ("v0", "v1", "v2", "v3") or (cfg.communication.fused_kernels and self.device.type == "cuda"
+                                                           and not self.baseline)) and comm.size > 1
+      shard_world = comm.size if self.sharded else 1
+      flat = FlatParameters(params, cfg.communication.max_splits, shard_world, allocator=self._bucket_allocator(comm))
+      self.flats[s] = flat
+      if comm.size > 1:
+        for dt, buf in flat.flat_params.items():
+          comm.broadcast(buf, root=0)
+        for b in self.stage_modules[s].buffers():
+          comm.broadcast(b, root=0)
+      opts = []
+      offload = cfg.offload.level == "v0"
+      for b in flat.buckets:
+        lo, hi = b.shard_range(comm.rank if self.sharded else 0, shard_world)
+        if b.dtype == torch.float32 and not offload:
+          master = b.flat_param[lo:hi]                     # fp32 weights are their own master copy
+        else:
+          master = b.flat_param[lo:hi].to(torch.float32)
+        mask = flat.decay_mask(b, self.no_decay)
+        if offload:
+          from easyparallellibrary_b200.runtime.offload import OffloadedOptimizer
+          opts.append(OffloadedOptimizer(self.opt_kind, self.hyper, master, None if mask is None else mask[lo:hi], self.device))
+        else:
+          opts.append(FlatOptimizer(self.opt_kind, self.hyper, master, None if mask is None else mask[lo:hi]))
+      self.optimizers[s] = opts
+    self._setup_fused(cfg)
+    self._install_grad_hooks()
+    if self.plan.pipeline:
+      from easyparallellibrary_b200.parallel.pipeline import PipelineExecutor
+      self.pipe = PipelineExecutor(self)
+    self._built = True
+    return self
+
+  def _bucket_allocator(self, comm):
+    return None
+
+  def _setup_fused(self, cfg) -> None:
+    """Fused reduce-scatter + Adam + all-gather over NVLink peer memory (K1)."""
+    self.fused = None
+    if self.device.type != "cuda" or self.baseline or not cfg.communication.fused_kernels:
+      return
+    try:
+      from easyparallellibrary_b200.parallel.fused_dp import FusedDataParallel
+    except ImportError:
+      return
+    self.fused = FusedDataParallel.maybe_create(self)
+
+  def _auto_stages(self, graph: Graph) -> None:
+    """auto.auto_parallel: cut the sequential layers into pipeline.num_stages taskgraphs."""
+    from easyparallellibrary_b200.ir.capture import trace_module_costs
+    from easyparallellibrary_b200.ir.node import Node
+    from easyparallellibrary_b200.parallel.planner import AutoStageGenerator
+    from easyparallellibrary_b200.strategies.base import Replicate
+    layers = sequential_layers(self.model)
+    if layers is None:
+      raise RuntimeError("auto.auto_parallel needs a sequential model")
+    n_stages = self.config.pipeline.num_stages
+    nodes = None
+    if self.example_inputs is not None:
+      try:
+        traced = trace_module_costs(self.model, self.example_inputs)
+        owner = {}
+        for li, l in enumerate(layers):
+          for m in l.modules():
+            owner[id(m)] = li
+        per_layer: Dict[int, Node] = {}
+        for n in traced:
+          li = owner.get(id(n.module))
+          if li is None:
+            continue
+          agg = per_layer.setdefault(li, Node(name="layer.%d" % li, type=type(layers[li]).__name__))
+          agg.flops += n.flops
+          agg.param_count += n.param_count
+          agg.act_bytes += n.act_bytes
+        nodes = [per_layer.get(i, Node(name="layer.%d" % i, type=type(layers[i]).__name__)) for i in range(len(layers))]
+      except Exception as e:  # pragma: no cover - tracing is best effort
+        get_logger().warning("auto stage tracing failed (%s); falling back to parameter counts", e)
+    if nodes is None:
+      nodes = [Node(name="layer.%d" % i, type=type(l).__name__, param_count=sum(p.numel() for p in l.parameters()))
+               for i, l in enumerate(layers)]
+    stages = AutoStageGenerator(num_stages=n_stages).search(nodes)
+    graph._taskgraphs = []
+    graph._by_strategy = {}
+    graph._param_tg.clear()
+    graph._module_tg.clear()
+    for s, st in enumerate(stages):
+      tg = graph.new_taskgraph(Replicate(1, name="auto_stage_%d" % s))
+      for n in st:
+        li = int(n.name.split(".")[1])
+        graph._module_tg[layers[li]] = tg.index
+        tg.add_module(layers[li])
+        for p in layers[li].parameters():
+          if p not in graph._param_tg:
+            graph._param_tg[p] = tg.index
+            tg.add_parameter(p)
+
+  def _assign_layers(self, layers: List[nn.Module], graph: Graph) -> List[int]:
+    stage_of_tg = {ti: s for s, ti in enumerate(self.plan.stage_taskgraphs)}
+    assign, cur = [], 0
+    for l in layers:
+      tg = graph.taskgraph_of(l)
+      if tg is not None and tg.index in stage_of_tg:
+        cur = max(cur, stage_of_tg[tg.index])     # stages are monotone in call order
+      assign.append(cur)
+    return assign
+
+  # ================================================================== gradient hooks
+  def _install_grad_hooks(self) -> None:
+    self._bucket_of: Dict[int, Tuple[int, Bucket, int]] = {}
+    self._overlap = False
+    self._first_micro_batch = True
+    self._last_micro_batch = True
+    for s, flat in self.flats.items():
+      for b in flat.buckets:
+        for p, o in zip(b.params, b.offsets):
+          self._bucket_of[id(p)] = (s, b, o)
+          p.register_post_accumulate_grad_hook(self._on_grad_ready)
+    self._pending: List[Tuple[int, Bucket, Any]] = []
+
+  def _on_grad_ready(self, p: nn.Parameter) -> None:
+    s, b, o = self._bucket_of[id(p)]
+    if p.grad is not None:
+      view = b.flat_grad[o:o + p.numel()].view(p.shape)
+      if p.grad.data_ptr() != view.data_ptr():       # autograd replaced the view: fold it back
+        view.add_(p.grad)
+        p.grad = view if view.dtype == p.dtype else None
+    b.ready += 1
+    if self._overlap and self._last_micro_batch and b.ready == len(b.params):
+      self._launch_bucket_reduce(s, b)
+
+  # ================================================================== one step
+  def step(self, *batch, **kwargs) -> StepOutput:
+    if not self._built:
+      self.build()
+    for h in self.hooks:
+      h.before_step(self)
+    cfg = self.config
+    M = cfg.pipeline.num_micro_batch
+    mean = cfg.communication.gradients_reduce_method == constant.REDUCE_MEAN
+    graph = Graph.get()
+    graph.pop_collections()
+    for flat in self.flats.values():
+      flat.zero_grad()
+    self._pending = []
+    batch = tuple(_to_device(x, self.device) for x in batch)
+    micro = _split_batch(batch, M)
+    losses: List[torch.Tensor] = []
+    collected: List["OrderedDict[str, List[Any]]"] = []
+    dp_size = max(c.size for c in self.dp_comms.values()) if self.dp_comms else 1
+    self._overlap = (dp_size > 1 and not cfg.communication.clip_after_allreduce and self.max_grad_norm is None
+                     and self.fused is None)
+    if self.plan.pipeline:
+      losses, collected = self.pipe.run(micro, mean)
+    else:
+      for i, mb in enumerate(micro):
+        self._first_micro_batch = i == 0
+        self._last_micro_batch = i == M - 1
+        with phase_scope(ModelPhase.FORWARD):
+          loss = self._forward_loss(mb, kwargs)
+        collected.append(graph.pop_collections())
+        losses.append(loss.detach())
+        scaled = self.scaler.scale(loss)
+        if mean and M > 1:
+          scaled = scaled / M
+        with phase_scope(ModelPhase.BACKWARD):
+          scaled.backward()
+    with phase_scope(ModelPhase.APPLY):
+      skipped, gnorm = self._reduce_and_apply(mean)
+    self.global_step += 0 if skipped else 1
+    out = StepOutput(skipped=skipped, grad_norm=gnorm, loss_scale=self.scaler.loss_scale)
+    if losses:
+      out.loss = torch.stack([l.float() for l in losses]).mean() if mean else torch.stack([l.float() for l in losses]).sum()
+    out.collections = self._merge_collections(collected)
+    for h in self.hooks:
+      h.after_step(self, out)
+    return out
+
+  def _forward_loss(self, mb: Tuple[Any, ...], kwargs) -> torch.Tensor:
+    if self.plan.num_stages > 1:          # colocated stages: run them back to back
+      x = mb[0]
+      for s in range(self.plan.num_stages):
+        x = self.stage_modules[s](x)
+      out = x
+      return self.loss_fn(out, *mb[1:]) if self.loss_fn is not None else _as_loss(out)
+    if self.loss_fn is not None:
+      return self.loss_fn(self.model(mb[0], **kwargs), *mb[1:])
+    return _as_loss(self.model(*mb, **kwargs))
+
+  # ------------------------------------------------------------------ reduce + apply
+  def _launch_bucket_reduce(self, s: int, b: Bucket) -> None:
+    comm = self.dp_comms[s]
+    if comm.size <= 1:
+      return
+    slot = len(self._pending) % comm.pool.size
+    be = comm.pool.backends[slot]
+    zero = self.config.zero.level
+    if self.sharded and zero != "v0":
+      lo, hi = b.shard_range(comm.rank, comm.size)
+      w = be.reduce_scatter_into(b.flat_grad[lo:hi], b.flat_grad, "sum", async_op=True)
+    else:
+      w = be.all_reduce_async(b.flat_grad, "sum")
+    self._pending.append((s, b, w))
+
+  def _reduce_and_apply(self, mean: bool) -> Tuple[bool, Optional[torch.Tensor]]:
+    cfg = self.config
+    clip_after = cfg.communication.clip_after_allreduce
+    inv = self.scaler.inv_scale
+    gnorm = None
+    if self.fused is not None:
+      return self.fused.reduce_and_apply(mean)
+    # (1) clip-then-reduce: local norm, local clip coefficient folded into the grad scale
+    local_coef = 1.0
+    if self.max_grad_norm is not None and not clip_after:
+      gnorm = self._grad_norm(reduced=False) * inv
+      local_coef = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
+    # (2) reduce, last bucket first (its gradients were produced first)
+    launched = {(s, b.index) for s, b, _ in self._pending}
+    for s in self.plan.local_stages:
+      for b in reversed(self.flats[s].buckets):
+        if (s, b.index) not in launched:
+          self._launch_bucket_reduce(s, b)
+    for _, _, w in self._pending:
+      if w is not None:
+        w.wait()
+    # (3) finite check (fp16 only), agreed on by every replica
+    found_inf = False
+    if isinstance(self.scaler, (amp_lib.DynamicLossScale, amp_lib.FixedLossScale)):
+      bad = torch.zeros(1, device=self.device)
+      for s in self.plan.local_stages:
+        for b in self.flats[s].buckets:
+          bad += (~torch.isfinite(b.flat_grad)).any().float()
+      for comm in self.dp_comms.values():
+        if comm.size > 1:
+          comm.primary.all_reduce(bad, "max")
+      found_inf = bool(bad.item() > 0)
+    if self.scaler.update(found_inf):
+      return True, gnorm
+    # (4) reduce-then-clip
+    coef = local_coef
+    if self.max_grad_norm is not None and clip_after:
+      n = max(c.size for c in self.dp_comms.values())
+      gnorm = self._grad_norm(reduced=True) * inv / (n if mean else 1)
+      coef = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
+    # (5) apply
+    for s in self.plan.local_stages:
+      comm, flat, opts = self.dp_comms[s], self.flats[s], self.optimizers[s]
+      scale = inv * coef / (comm.size if mean else 1)
+      groups = max(1, cfg.optimizer.num_apply_group)
+      gathers = []
+      for b, opt in zip(flat.buckets, opts):
+        lo, hi = b.shard_range(comm.rank if self.sharded else 0, comm.size if self.sharded else 1)
+        gshard, pshard = b.flat_grad[lo:hi], b.flat_param[lo:hi]
+        if self.baseline:
+          self._baseline_apply(opt, gshard, pshard, scale)
+        else:
+          n = hi - lo
+          per = (n + groups - 1) // groups
+          for g in range(groups - 1, -1, -1):           # groups applied last to first (optimizer_helper.py:95-120)
+            opt.step(gshard, pshard, scale, g * per, min((g + 1) * per, n), count_step=(g == groups - 1))
+        if self.sharded and comm.size > 1:
+          gathers.append(comm.pool.backends[len(gathers) % comm.pool.size].all_gather_into(b.flat_param, pshard, async_op=True))
+      for w in gathers:
+        if w is not None:
+          w.wait()
+    return False, gnorm
+
+  def _baseline_apply(self, opt: FlatOptimizer, g, p, scale) -> None:
+    from easyparallellibrary_b200.runtime.optimizer import adamw_reference, sgd_reference
+    opt.step_count += 1
+    out = p if p.data_ptr() != opt.master.data_ptr() else None
+    if opt.kind == "sgd":
+      sgd_reference(opt.master, g, opt.m, opt.hyper, scale, out)
+    else:
+      adamw_reference(opt.master, g, opt.m, opt.v, opt.step_count, opt.hyper, scale, opt.decay_mask, out)
+
+  def _grad_norm(self, reduced: bool) -> torch.Tensor:
+    sq = torch.zeros(1, device=self.device, dtype=torch.float32)
+    for s in self.plan.local_stages:
+      comm = self.dp_comms[s]
+      part = torch.zeros(1, device=self.device, dtype=torch.float32)
+      for b in self.flats[s].buckets:
+        if reduced and self.sharded and self.config.zero.level != "v0" and comm.size > 1:
+          lo, hi = b.shard_range(comm.rank, comm.size)
+          part += b.flat_grad[lo:hi].float().pow(2).sum()
+        else:
+          part += b.flat_grad.float().pow(2).sum()
+      if reduced and self.sharded and self.config.zero.level != "v0" and comm.size > 1:
+        comm.primary.all_reduce(part, "sum")
+      sq += part
+    if self.plan.pipeline and self.plan.num_stages > 1:
+      sq = self.pipe.all_reduce_over_stages(sq)
+    return sq.sqrt()
+
+  # ------------------------------------------------------------------ collections
+  def _merge_collections(self, collected: List["OrderedDict[str, List[Any]]"]) -> "OrderedDict[str, List[Any]]":
+    """LOCAL_*: merge over micro-batches; GLOBAL_*: additionally over replicas."""
+    merged: "OrderedDict[str, List[Any]]" = OrderedDict()
+    if not collected or not any(collected):
+      return merged
+    keys = [k for k in GraphKeys.ALL_COLLECTION_KEYS if any(k in c for c in collected)]
+    comm = next(iter(self.dp_comms.values())) if self.dp_comms else None
+    for k in keys:
+      per_mb = [c[k] for c in collected if k in c]
+      n_obj = min(len(x) for x in per_mb)
+      outs = []
+      for j in range(n_obj):
+        vals = [torch.as_tensor(x[j]).detach() for x in per_mb]
+        vals = [v.to(self.device) for v in vals]
+        if "concat" in k:
+          v = torch.cat([t.reshape(1) if t.dim() == 0 else t for t in vals], 0)
+        elif "mean" in k:
+          v = torch.stack([t.float() for t in vals]).mean(0)
+        else:
+          v = torch.stack(vals).sum(0)
+        if k.startswith("global") and comm is not None and comm.size > 1:
+          if "concat" in k:
+            v = comm.allgather(v.contiguous())
+          else:
+            v = comm.allreduce(v.contiguous(), mean="mean" in k)
+        outs.append(v)
+      merged[k] = outs
+    return merged
+
+  # ------------------------------------------------------------------ evaluation & state
+  @torch.no_grad()
+  def eval_step(self, *batch, **kwargs):
+    """Evaluation is not parallelised (reference ``ir/graph.py:926-933``): plain forward."""
+    if not self._built:
+      self.build()
+    batch = tuple(_to_device(x, self.device) for x in batch)
+    was = self.model.training
+    self.model.eval()
+    try:
+      if self.plan.pipeline:
+        return self.pipe.forward_only(batch)
+      return self._forward_loss(batch, kwargs)
+    finally:
+      self.model.train(was)
+
+  def state_dict(self) -> Dict[str, Any]:
+    sd = {"global_step": self.global_step, "model": {}, "optim": {}, "loss_scale": self.scaler.loss_scale}
+    for s in self.plan.local_stages:
+      sd["model"][s] = self.stage_modules[s].state_dict()
+      sd["optim"][s] = [o.state_dict() for o in self.optimizers[s]]
+    return sd
+
+  def load_state_dict(self, sd: Dict[str, Any]) -> None:
+    self.global_step = int(sd["global_step"])
+    if hasattr(self.scaler, "loss_scale"):
+      self.scaler.loss_scale = sd.get("loss_scale", self.scaler.loss_scale)
+    for s in self.plan.local_stages:
+      self.stage_modules[s].load_state_dict(sd["model"][s])
+      for o, osd in zip(self.optimizers[s], sd["optim"][s]):
+        o.load_state_dict(osd)
+
+  @property
+  def is_first_replica(self) -> bool:
+    return all(c.rank == 0 for c in self.dp_comms.values())
+
+
+def _as_loss(out) -> torch.Tensor:
+  if isinstance(out, torch.Tensor):
+    return out
+  if isinstance(out, dict):
+    return out["loss"]
+  if isinstance(out, (tuple, list)):
+    return out[0]
+  raise TypeError("model output %r cannot be interpreted as a loss" % type(out))
+
+
+def _to_device(x, device):
+  if isinstance(x, torch.Tensor) and x.device != device:
+    return x.to(device, non_blocking=True)
+  return x
+
+
+def _materialize(module: nn.Module, device: torch.device) -> None:
+  """Move to ``device``; parameters created on the meta device are allocated and re-initialised."""
+  has_meta = any(p.is_meta for p in module.parameters())
+  if has_meta:
+    module.to_empty(device=device)
+    for m in module.modules():
+      reset = getattr(m, "reset_parameters", None)
+      if callable(reset):
+        reset()
+  else:
+    module.to(device)
+
+
+def prepare(model: nn.Module, optimizer: str = "adamw", **kw) -> Trainer:
+  """Functional spelling of ``Trainer(...).build()``."""
+  return Trainer(model, optimizer, **kw).build()

@@ -1,0 +1,163 @@
+// Fused bias + GELU (tanh approximation, as GPT-2/BERT use) forward and backward, plus bias-gradient
+// column reduction.  Element-wise, HBM-bound; in the GEMM path these run as the tcgen05 epilogue
+// (gemm_tcgen05.cu), the stand-alone kernels serve non-GEMM call sites and are the numerics reference.
+#include "epl_common.cuh"
+#include <algorithm>
+
+namespace epl {
+
+EPL_DEVICE float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+EPL_DEVICE float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  float t = tanhf(u);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x * x);
+}
+
+// y = gelu(x + bias); pre = x + bias (optional, saved for backward).  x:[rows, D], bias:[D]
+template <typename T, bool kSavePre>
+__global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const T* __restrict__ x, const T* __restrict__ bias,
+                                                            T* __restrict__ y, T* __restrict__ pre, int64_t nvec, int dvec) {
+  constexpr int E = 16 / sizeof(T);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    Vec<T, E> xv = ld_vec<T, E>(x + i * E);
+    Vec<T, E> o, p;
+    if (bias != nullptr) {
+      Vec<T, E> bv = ld_vec<T, E>(bias + (i % dvec) * E);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float h = to_f32<T>(xv.v[e]) + to_f32<T>(bv.v[e]);
+        p.v[e] = from_f32<T>(h);
+        o.v[e] = from_f32<T>(gelu_tanh(to_f32<T>(p.v[e])));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) { p.v[e] = xv.v[e]; o.v[e] = from_f32<T>(gelu_tanh(to_f32<T>(xv.v[e]))); }
+    }
+    st_vec<T, E>(y + i * E, o);
+    if constexpr (kSavePre) st_vec<T, E>(pre + i * E, p);
+  }
+}
+
+// dpre = dy * gelu'(pre)
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ pre, const T* __restrict__ dy,
+                                                       T* __restrict__ dpre, int64_t nvec) {
+  constexpr int E = 16 / sizeof(T);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    Vec<T, E> pv = ld_vec<T, E>(pre + i * E);
+    Vec<T, E> dv = ld_vec<T, E>(dy + i * E);
+    Vec<T, E> o;
+#pragma unroll
+    for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>(to_f32<T>(dv.v[e]) * gelu_tanh_grad(to_f32<T>(pv.v[e])));
+    st_vec<T, E>(dpre + i * E, o);
+  }
+}
+
+// column sums: out[d] (+)= sum_r x[r][d].  grid = (ceil(D/64), row_chunks); partial sums via atomicAdd on fp32 scratch.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ scratch, int rows, int D) {
+  // block: 64 columns x 4 row-lanes; 2 columns per thread in x (bf16x2) -> threads.x = 32, threads.y = 8
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 2;
+  float a0 = 0.f, a1 = 0.f;
+  if (col < D) {
+    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < rows; r += gridDim.y * blockDim.y) {
+      const T* p = x + (size_t)r * D + col;
+      a0 += to_f32<T>(p[0]);
+      if (col + 1 < D) a1 += to_f32<T>(p[1]);
+    }
+  }
+  __shared__ float s[8][64];
+  s[threadIdx.y][threadIdx.x * 2] = a0;
+  s[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a0 += s[k][threadIdx.x * 2]; a1 += s[k][threadIdx.x * 2 + 1]; }
+    if (col < D) atomicAdd(&scratch[col], a0);
+    if (col + 1 < D) atomicAdd(&scratch[col + 1], a1);
+  }
+}
+
+template <typename T>
+__global__ void finish_colsum_kernel(const float* __restrict__ scratch, T* __restrict__ out, int D, int accumulate) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) {
+    float v = scratch[d];
+    if (accumulate) v += to_f32<T>(out[d]);
+    out[d] = from_f32<T>(v);
+  }
+}
+
+// y = a + b (residual add), 16-byte vectors
+template <typename T>
+__global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t nvec) {
+  constexpr int E = 16 / sizeof(T);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    Vec<T, E> av = ld_vec<T, E>(a + i * E), bv = ld_vec<T, E>(b + i * E), o;
+#pragma unroll
+    for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>(to_f32<T>(av.v[e]) + to_f32<T>(bv.v[e]));
+    st_vec<T, E>(y + i * E, o);
+  }
+}
+
+static int grid_for(int64_t nvec) { return (int)std::max<int64_t>(1, std::min<int64_t>((nvec + 255) / 256, (int64_t)kNumSMs * 16)); }
+
+}  // namespace epl
+using namespace epl;
+
+#define BY_DTYPE(dtype, ...)                                           \
+  if (dtype == EPL_F32) { using T = float; __VA_ARGS__; }              \
+  else if (dtype == EPL_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }\
+  else { using T = __half; __VA_ARGS__; }
+
+// n = rows*D elements; D and n must be multiples of 16/sizeof(T)
+extern "C" int epl_bias_gelu_fwd(const void* x, const void* bias, void* y, void* pre, int64_t n, int D, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BY_DTYPE(dtype, {
+    constexpr int E = 16 / sizeof(T);
+    int64_t nvec = n / E;
+    if (pre) bias_gelu_fwd_kernel<T, true><<<grid_for(nvec), 256, 0, st>>>((const T*)x, (const T*)bias, (T*)y, (T*)pre, nvec, D / E);
+    else bias_gelu_fwd_kernel<T, false><<<grid_for(nvec), 256, 0, st>>>((const T*)x, (const T*)bias, (T*)y, nullptr, nvec, D / E);
+  });
+  return EPL_CHECK_LAUNCH();
+}
+
+extern "C" int epl_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BY_DTYPE(dtype, {
+    constexpr int E = 16 / sizeof(T);
+    int64_t nvec = n / E;
+    gelu_bwd_kernel<T><<<grid_for(nvec), 256, 0, st>>>((const T*)pre, (const T*)dy, (T*)dpre, nvec);
+  });
+  return EPL_CHECK_LAUNCH();
+}
+
+// scratch: D floats, zeroed by this call
+extern "C" int epl_colsum(const void* x, void* out, void* scratch, int rows, int D, int dtype, int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, (size_t)D * sizeof(float), st);
+  dim3 block(32, 8), grid((D + 63) / 64, std::max(1, std::min((rows + 63) / 64, 64)));
+  BY_DTYPE(dtype, {
+    colsum_kernel<T><<<grid, block, 0, st>>>((const T*)x, (float*)scratch, rows, D);
+    finish_colsum_kernel<T><<<(D + 255) / 256, 256, 0, st>>>((const float*)scratch, (T*)out, D, accumulate);
+  });
+  return EPL_CHECK_LAUNCH();
+}
+
+extern "C" int epl_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BY_DTYPE(dtype, {
+    constexpr int E = 16 / sizeof(T);
+    int64_t nvec = n / E;
+    add_kernel<T><<<grid_for(nvec), 256, 0, st>>>((const T*)a, (const T*)b, (T*)y, nvec);
+  });
+  return EPL_CHECK_LAUNCH();
+}

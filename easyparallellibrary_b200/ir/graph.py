@@ -23,6 +23,37 @@ from easyparallellibrary_b200.ir.taskgraph import Taskgraph
 from easyparallellibrary_b200.strategies.base import ParallelStrategy, Replicate, Split
 
 
+class _IdMap(object):
+  """Identity-keyed weak map (tensors cannot live in a WeakKeyDictionary: ``==`` is element-wise)."""
+
+  def __init__(self):
+    self._d: Dict[int, Any] = {}
+
+  def _drop(self, key):
+    self._d.pop(key, None)
+
+  def __contains__(self, obj) -> bool:
+    return id(obj) in self._d
+
+  def __setitem__(self, obj, value) -> None:
+    key = id(obj)
+    try:
+      ref = weakref.ref(obj, lambda _r, k=key: self._drop(k))
+    except TypeError:
+      ref = None
+    self._d[key] = (ref, value)
+
+  def __getitem__(self, obj):
+    return self._d[id(obj)][1]
+
+  def get(self, obj, default=None):
+    hit = self._d.get(id(obj))
+    return default if hit is None else hit[1]
+
+  def clear(self) -> None:
+    self._d.clear()
+
+
 class GraphKeys(object):
   """Collections whose members are merged over micro-batches (LOCAL_*) and
   additionally over replicas (GLOBAL_*)."""
@@ -43,8 +74,8 @@ class Graph(object):
   def __init__(self):
     self._taskgraphs: List[Taskgraph] = []
     self._by_strategy: Dict[int, Taskgraph] = {}
-    self._param_tg: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
-    self._module_tg: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+    self._param_tg = _IdMap()
+    self._module_tg = _IdMap()
     self._collections: "OrderedDict[str, List[Any]]" = OrderedDict()
     self._nodes: List[Node] = []
     self.training = True

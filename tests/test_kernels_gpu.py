@@ -1,0 +1,210 @@
+"""Numerics of every sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _close(a, b, rtol, atol, what=""):
+  a, b = a.float(), b.float()
+  err = (a - b).abs()
+  tol = atol + rtol * b.abs()
+  bad = (err > tol).float().mean().item()
+  assert bad < 1e-3, "%s: %.4f%% elements out of tolerance, max err %.4g (ref max %.4g)" % (
+      what, bad * 100, err.max().item(), b.abs().max().item())
+
+
+@pytest.mark.parametrize("gdt,odt", [(torch.bfloat16, torch.bfloat16), (torch.float32, None), (torch.float16, torch.float16)])
+def test_adamw(gdt, odt):
+  from easyparallellibrary_b200.ops import fused_optim
+  from easyparallellibrary_b200.runtime.optimizer import AdamHyper, adamw_reference
+  torch.manual_seed(0)
+  n = 1_000_003 if gdt == torch.float32 else 1 << 20
+  master = torch.randn(n, device=DEV)
+  grad = (torch.randn(n, device=DEV) * 3).to(gdt)
+  m, v = torch.rand(n, device=DEV) * 0.1, torch.rand(n, device=DEV) * 0.1
+  mask = (torch.rand(n, device=DEV) > 0.3).float()
+  out = torch.empty(n, device=DEV, dtype=odt) if odt else None
+  h = AdamHyper(lr=1e-2, weight_decay=0.1)
+  rm, rmm, rv = master.clone(), m.clone(), v.clone()
+  rout = torch.empty(n, device=DEV, dtype=odt) if odt else None
+  adamw_reference(rm, grad, rmm, rv, 3, h, 0.5, mask, rout)
+  fused_optim.adamw_step(master, grad, m, v, 3, h, 0.5, mask, out)
+  _close(master, rm, 1e-5, 1e-6, "master")
+  _close(m, rmm, 1e-5, 1e-6, "m")
+  _close(v, rv, 1e-5, 1e-6, "v")
+  if odt:
+    _close(out, rout, 1e-2, 1e-3, "out")
+
+
+def test_sgd_and_sumsq():
+  from easyparallellibrary_b200.ops import fused_optim
+  from easyparallellibrary_b200.runtime.optimizer import SGDHyper, sgd_reference
+  n = 100_001
+  master, grad, mom = torch.randn(n, device=DEV), torch.randn(n, device=DEV).bfloat16(), torch.randn(n, device=DEV)
+  rm, rmom = master.clone(), mom.clone()
+  h = SGDHyper(lr=0.1, momentum=0.9, weight_decay=0.01)
+  out, rout = torch.empty(n, device=DEV, dtype=torch.bfloat16), torch.empty(n, device=DEV, dtype=torch.bfloat16)
+  sgd_reference(rm, grad, rmom, h, 2.0, rout)
+  fused_optim.sgd_step(master, grad, mom, h, 2.0, out)
+  _close(master, rm, 1e-5, 1e-6, "sgd")
+  s = fused_optim.sumsq_and_finite(grad)
+  assert abs(s[0].item() - grad.float().pow(2).sum().item()) / s[0].item() < 1e-3 and s[1].item() == 0
+  grad[7] = float("inf")
+  assert fused_optim.sumsq_and_finite(grad)[1].item() == 1.0
+
+
+@pytest.mark.parametrize("D", [768, 1600, 4096])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_layernorm(D, dt):
+  from easyparallellibrary_b200.ops.layernorm import layer_norm, rms_norm
+  torch.manual_seed(0)
+  rows = 1000
+  x = (torch.randn(rows, D, device=DEV) * 2 + 0.5).to(dt).requires_grad_()
+  g = (torch.rand(D, device=DEV) + 0.5).to(dt).requires_grad_()
+  b = torch.randn(D, device=DEV).to(dt).requires_grad_()
+  dy = torch.randn(rows, D, device=DEV).to(dt)
+  y = layer_norm(x, g, b)
+  y.backward(dy)
+  xf, gf, bf = x.detach().float().requires_grad_(), g.detach().float().requires_grad_(), b.detach().float().requires_grad_()
+  yr = torch.nn.functional.layer_norm(xf, (D,), gf, bf)
+  yr.backward(dy.float())
+  tol = (2e-2, 2e-2) if dt == torch.bfloat16 else (1e-4, 1e-4)
+  _close(y, yr, *tol, "ln y")
+  _close(x.grad, xf.grad, *tol, "ln dx")
+  _close(g.grad, gf.grad, tol[0], tol[1] * 30, "ln dgamma")
+  _close(b.grad, bf.grad, tol[0], tol[1] * 30, "ln dbeta")
+  x.grad = None
+  y2 = rms_norm(x, g)
+  y2.backward(dy)
+  xf.grad = None
+  yr2 = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * gf
+  yr2.backward(dy.float())
+  _close(y2, yr2, *tol, "rms y")
+  _close(x.grad, xf.grad, *tol, "rms dx")
+
+
+def test_xent():
+  from easyparallellibrary_b200.ops.cross_entropy import softmax_cross_entropy
+  torch.manual_seed(0)
+  rows, V = 300, 50304
+  logits = (torch.randn(rows, V, device=DEV) * 3).bfloat16()
+  labels = torch.randint(0, V, (rows,), device=DEV)
+  labels[5] = -100
+  ref_in = logits.float().requires_grad_()
+  ref = torch.nn.functional.cross_entropy(ref_in, labels, ignore_index=-100)
+  (ref * 2).backward()
+  mine_in = logits.clone().requires_grad_()
+  loss = softmax_cross_entropy(mine_in, labels)
+  (loss * 2).backward()
+  assert abs(loss.item() - ref.item()) < 2e-3 * abs(ref.item())
+  _close(mine_in.grad, ref_in.grad, 2e-2, 1e-6, "dlogits")
+
+
+CASES = [  # (M, N, K)
+    (256, 256, 128), (128, 160, 64), (384, 512, 320), (1000, 1600, 1600), (2048, 6400, 1600), (333, 264, 200),
+]
+
+
+@pytest.mark.parametrize("M,N,K", CASES)
+@pytest.mark.parametrize("layout", ["nt", "nn", "tn"])
+def test_gemm_layouts(M, N, K, layout):
+  from easyparallellibrary_b200.ops.linear import gemm
+  torch.manual_seed(0)
+  K = (K + 7) // 8 * 8
+  if layout == "nt":      # D = A[M,K] @ B[N,K]^T
+    a, b = torch.randn(M, K, device=DEV).bfloat16(), torch.randn(N, K, device=DEV).bfloat16()
+    ref = a.float() @ b.float().t()
+    out = gemm(a, b)
+  elif layout == "nn":    # D = A[M,K] @ B[K,N]
+    N = (N + 7) // 8 * 8
+    a, b = torch.randn(M, K, device=DEV).bfloat16(), torch.randn(K, N, device=DEV).bfloat16()
+    ref = a.float() @ b.float()
+    out = gemm(a, b, b_mn_major=True)
+  else:                   # D = A[K,M]^T @ B[K,N]
+    M, N = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    a, b = torch.randn(K, M, device=DEV).bfloat16(), torch.randn(K, N, device=DEV).bfloat16()
+    ref = a.float().t() @ b.float()
+    out = gemm(a, b, a_mn_major=True, b_mn_major=True)
+  _close(out, ref, 1e-2, 1e-2 * math.sqrt(K), "gemm %s" % layout)
+
+
+@pytest.mark.parametrize("bn", [128, 160, 256])
+def test_gemm_tile_widths_and_epilogues(bn):
+  from easyparallellibrary_b200.ops import linear as L
+  torch.manual_seed(1)
+  M, N, K = 512, 1280, 512
+  a, b = torch.randn(M, K, device=DEV).bfloat16(), (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+  bias = torch.randn(N, device=DEV).bfloat16()
+  L._FORCE_BN = bn
+  try:
+    ref = a.float() @ b.float().t() + bias.float()
+    _close(L.gemm(a, b, bias=bias, epilogue=L.EPI_BIAS), ref, 1e-2, 5e-2, "bias")
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    act = L.gemm(a, b, bias=bias, epilogue=L.EPI_BIAS_GELU, pre=pre)
+    _close(pre, ref, 1e-2, 5e-2, "pre")
+    _close(act, torch.nn.functional.gelu(pre.float(), approximate="tanh"), 1e-2, 2e-2, "gelu")
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    _close(L.gemm(a, b, bias=bias, epilogue=L.EPI_BIAS_RESIDUAL, aux=res), ref + res.float(), 1e-2, 5e-2, "residual")
+    x = pre.float().requires_grad_()
+    torch.nn.functional.gelu(x, approximate="tanh").sum().backward()
+    _close(L.gemm(a, b, epilogue=L.EPI_DGELU, aux=pre), (a.float() @ b.float().t()) * x.grad, 1e-2, 5e-2, "dgelu")
+    acc = torch.randn(M, N, device=DEV)
+    expect = acc + a.float() @ b.float().t()
+    _close(L.gemm(a, b, out=acc, accumulate=True), expect, 1e-2, 5e-2, "accumulate fp32")
+  finally:
+    L._FORCE_BN = 0
+
+
+def test_linear_and_mlp_autograd():
+  from easyparallellibrary_b200.ops.linear import linear, mlp
+  torch.manual_seed(2)
+  B, S, d = 4, 96, 256
+  x = torch.randn(B, S, d, device=DEV).bfloat16().requires_grad_()
+  w1 = (torch.randn(4 * d, d, device=DEV) * 0.05).bfloat16().requires_grad_()
+  b1 = torch.randn(4 * d, device=DEV).bfloat16().requires_grad_()
+  w2 = (torch.randn(d, 4 * d, device=DEV) * 0.05).bfloat16().requires_grad_()
+  b2 = torch.randn(d, device=DEV).bfloat16().requires_grad_()
+  dy = torch.randn(B, S, d, device=DEV).bfloat16()
+  y = mlp(x, w1, b1, w2, b2)
+  y.backward(dy)
+  f = [t.detach().float().requires_grad_() for t in (x, w1, b1, w2, b2)]
+  yr = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(f[0], f[1], f[2]), approximate="tanh"), f[3], f[4])
+  yr.backward(dy.float())
+  _close(y, yr, 2e-2, 5e-2, "mlp y")
+  for name, t, r in zip(("dx", "dw1", "db1", "dw2", "db2"), (x, w1, b1, w2, b2), f):
+    _close(t.grad, r.grad, 3e-2, 3e-2 * r.grad.abs().max().item(), "mlp " + name)
+  x.grad = None
+  w = (torch.randn(3 * d, d, device=DEV) * 0.05).bfloat16().requires_grad_()
+  y = linear(x, w, None)
+  y.backward(torch.ones_like(y))
+  _close(w.grad, (torch.ones(B * S, 3 * d, device=DEV).t() @ x.detach().float().view(-1, d)), 2e-2, 0.5, "linear dw")
+
+
+def test_gpt2_tiny_step_matches_torch():
+  """One training step of GPT-2-tiny through the engine on the kernels vs the same model on torch fp32 ops."""
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config
+  torch.manual_seed(0)
+  epl.init(epl.Config({"amp.level": "bf16"}))
+  with epl.replicate(1):
+    model = GPT2(GPT2Config.named("tiny"))
+  ref = GPT2(GPT2Config.named("tiny"))
+  ref.load_state_dict(model.state_dict())
+  tr = epl.Trainer(model, "adamw", lr=1e-3)
+  idx = torch.randint(0, 512, (8, 128), device=DEV)
+  losses = [tr.step(idx, idx).item() for _ in range(5)]
+  opt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=0.01)
+  ref_losses = []
+  for _ in range(5):
+    loss = ref(idx.cpu(), idx.cpu())
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    ref_losses.append(loss.item())
+  assert losses[-1] < losses[0]
+  for a, b in zip(losses, ref_losses):
+    assert abs(a - b) < 0.05 * abs(b) + 0.05, (losses, ref_losses)

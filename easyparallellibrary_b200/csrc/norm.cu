@@ -183,7 +183,7 @@ static int launch_fwd(const void* x, const void* g, const void* b, void* y, floa
 #define LAUNCH(V)                                                                                                  \
   norm_fwd_kernel<T, V, kRms><<<grid, kWarpsPerCta * 32, 0, st>>>(xp, gp, bp, yp, mean, rstd, rows, D, eps)
   if (vpl <= 1) LAUNCH(1); else if (vpl <= 2) LAUNCH(2); else if (vpl <= 4) LAUNCH(4); else if (vpl <= 8) LAUNCH(8);
-  else if (vpl <= 16) LAUNCH(16); else return -2;
+  else if (vpl <= 16) LAUNCH(16); else if (vpl <= 32) LAUNCH(32); else return -2;
 #undef LAUNCH
   return EPL_CHECK_LAUNCH();
 }
@@ -197,7 +197,7 @@ static int launch_bwd(const void* x, const void* dy, const void* g, const float*
   const T *xp = (const T*)x, *dp = (const T*)dy, *gp = (const T*)g;
   T* dxp = (T*)dx;
 #define LAUNCH(V) norm_bwd_kernel<T, V, kRms><<<grid, kBwdThreads, 0, st>>>(xp, dp, gp, mean, rstd, dxp, pg, pb, rows, D)
-  if (vpt <= 1) LAUNCH(1); else if (vpt <= 2) LAUNCH(2); else if (vpt <= 4) LAUNCH(4); else return -2;
+  if (vpt <= 1) LAUNCH(1); else if (vpt <= 2) LAUNCH(2); else if (vpt <= 4) LAUNCH(4); else if (vpt <= 8) LAUNCH(8); else return -2;
 #undef LAUNCH
   return EPL_CHECK_LAUNCH();
 }

@@ -89,12 +89,17 @@ def build_stage_program(policy: str, stage: int, num_stages: int, num_micro_batc
   prog: List[Instr] = []
   posted = set()
   for i, (pre, ins, post) in enumerate(slots):
-    # post this slot's receives (if not already) and look ahead
-    for j in range(i, min(i + 1 + max(prefetch, 0), len(slots))):
-      for r in slots[j][0]:
-        if (r.op, r.mb) not in posted:
-          posted.add((r.op, r.mb))
-          prog.append(r)
+    # post this slot's receives (if not already) plus those of the next `prefetch` slots that receive anything
+    ahead, j = 0, i
+    while j < len(slots) and ahead <= max(prefetch, 0):
+      if slots[j][0] or j == i:
+        for r in slots[j][0]:
+          if (r.op, r.mb) not in posted:
+            posted.add((r.op, r.mb))
+            prog.append(r)
+        if j > i:
+          ahead += 1
+      j += 1
     prog.append(ins)
     prog.extend(post)
   if with_reduce:

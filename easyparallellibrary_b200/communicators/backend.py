@@ -58,11 +58,33 @@ class LocalBackend(object):
   def close(self): return None
 
 
+_GROUPS = {}       # (ranks tuple, copy index) -> ProcessGroup, filled collectively by register_groups()
+
+
+def register_groups(rank_lists: Sequence[Sequence[int]], copies: int = 1) -> None:
+  """``dist.new_group`` is collective over the whole world and order sensitive: every rank must call this with
+  the same list (the engine derives it from the plan, which is identical everywhere)."""
+  if not dist.is_initialized():
+    return
+  world = list(range(dist.get_world_size()))
+  for ranks in rank_lists:
+    ranks = list(ranks)
+    for c in range(copies):
+      key = (tuple(ranks), c)
+      if key in _GROUPS or len(ranks) <= 1:
+        continue
+      _GROUPS[key] = dist.group.WORLD if (ranks == world and c == 0) else dist.new_group(ranks)
+
+
+def reset_groups() -> None:
+  _GROUPS.clear()
+
+
 class TorchBackend(object):
   """A communicator over ``ranks`` (global ranks, ordered)."""
   name = "torch"
 
-  def __init__(self, ranks: Sequence[int], group=None):
+  def __init__(self, ranks: Sequence[int], group=None, copy: int = 0):
     if not dist.is_initialized():
       raise RuntimeError("torch.distributed is not initialised; call epl.init() under a launcher "
                          "(torchrun / epl-launch) or use a single-rank communicator")
@@ -71,7 +93,9 @@ class TorchBackend(object):
     me = dist.get_rank()
     self.rank = self.ranks.index(me) if me in self.ranks else -1
     if group is None:
-      if self.ranks == list(range(dist.get_world_size())):
+      group = _GROUPS.get((tuple(self.ranks), copy))
+    if group is None:
+      if self.ranks == list(range(dist.get_world_size())) and copy == 0:
         group = dist.group.WORLD
       else:
         group = dist.new_group(self.ranks)
@@ -204,11 +228,11 @@ class TorchBackend(object):
     self.group = None
 
 
-def make_backend(ranks: Sequence[int], prefer_native: bool = False, device: Optional[torch.device] = None):
+def make_backend(ranks: Sequence[int], prefer_native: bool = False, device: Optional[torch.device] = None, copy: int = 0):
   ranks = list(ranks)
   if len(ranks) <= 1:
     return LocalBackend(ranks or [0])
   if prefer_native and device is not None and device.type == "cuda":
     from easyparallellibrary_b200.communicators.native import NativeBackend
     return NativeBackend(ranks, device)
-  return TorchBackend(ranks)
+  return TorchBackend(ranks, copy=copy)

@@ -37,7 +37,7 @@ class CollectiveCommunicator(object):
     self.wire_dtype = wire_dtype
     self.device = device
     n = max(1, self.num_communicators if len(self.ranks) > 1 else 1)
-    self.pool = CommunicationPool([make_backend(self.ranks, prefer_native, device) for _ in range(n)])
+    self.pool = CommunicationPool([make_backend(self.ranks, prefer_native, device, copy=c) for c in range(n)])
     Env.get().comm_resources["%s#%d" % (name, len(Env.get().comm_resources))] = self
 
   # -- introspection -------------------------------------------------------------------

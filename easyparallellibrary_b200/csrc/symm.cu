@@ -1,0 +1,266 @@
+// Symmetric memory over NVLink peer mappings + the fused data-parallel kernel (K1).
+//
+// Symmetric memory: every rank cudaMalloc's an identically sized buffer, exports it with
+// cudaIpcGetMemHandle, the 64-byte handles travel through the control plane (torch.distributed
+// store) and every rank maps every peer's buffer (cudaIpcOpenMemHandle, lazy peer access).
+// Kernels then receive a table of peer pointers and use plain 16-byte ld/st.global over
+// NVLink-5 / NVSwitch (measured ~770 GB/s per direction per GPU).
+//
+// K1 — epl_fused_rs_adam_ag: ONE kernel per gradient bucket that replaces the reference's
+//   all-reduce (ncclAllReduce per fused buffer, graph_editor.py:670-725) + divide + unfused Adam,
+//   or its ZeRO-v1 reduce -> apply -> broadcast chain (runtime/zero.py:88-175):
+//     1. cross-GPU barrier (release/acquire flags in peer memory): every rank's gradients are ready;
+//     2. each rank owns 1/W of the bucket; for its shard it loads the W partial gradients straight
+//        from the peers' bucket buffers (reduce-scatter by P2P loads), un-scales, applies AdamW on
+//        its fp32 master/m/v shard, and stores the new bf16 weights into EVERY rank's parameter
+//        buffer (all-gather by P2P stores);
+//     3. cross-GPU barrier: all parameter shards have landed.
+//   Gradients cross NVLink once (W-1)/W * bucket bytes in, weights once out — the collective's
+//   minimum — and never touch HBM in between: no reduced-gradient buffer, no separate Adam pass.
+#include "epl_common.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+
+namespace epl {
+
+constexpr int kMaxPeers = 8;
+
+struct PeerTable {
+  void* ptr[kMaxPeers];
+};
+
+struct FusedDpArgs {
+  PeerTable grads;          // bucket gradient buffer of every rank (element type G)
+  PeerTable params;         // bucket parameter buffer of every rank (element type O)
+  PeerTable flags;          // uint32 flags[2][kMaxPeers] of every rank (this bucket's slot)
+  uint32_t* local_sync;     // [0] = go flag, [1] = arrival counter (device-local)
+  float* master; float* m; float* v; const float* mask;   // this rank's fp32 shard state
+  int64_t shard_start;      // element offset of this rank's shard inside the bucket
+  int64_t shard_n;          // elements in the shard (multiple of 8)
+  int rank, world;
+  uint32_t epoch;           // strictly increasing per launch on this bucket
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, inv_c1, inv_c2;
+};
+
+// ---- cross-GPU barrier executed by one CTA; the rest of the grid waits on a device-local flag -------------
+EPL_DEVICE void barrier_start(const FusedDpArgs& a) {
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      uint32_t* peer = reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]);
+      st_release_sys(peer + a.rank, a.epoch);                           // slot 0: "my gradients are ready"
+      const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]);
+      while (ld_acquire_sys(mine + threadIdx.x) < a.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.local_sync), "r"(a.epoch) : "memory");
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      uint32_t v;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.local_sync) : "memory"); } while (v < a.epoch);
+    }
+  }
+  __syncthreads();
+}
+
+EPL_DEVICE void barrier_end(const FusedDpArgs& a) {
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                              // my P2P stores are visible system-wide
+    uint32_t prev = atomicAdd(a.local_sync + 1, 1u);
+    is_last = (prev == gridDim.x * a.epoch - 1);                         // counter is never reset: epoch * grid arrivals
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      uint32_t* peer = reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]);
+      st_release_sys(peer + kMaxPeers + a.rank, a.epoch);                // slot 1: "my shard is written everywhere"
+      const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]);
+      while (ld_acquire_sys(mine + kMaxPeers + threadIdx.x) < a.epoch) {}
+    }
+  }
+}
+
+template <typename T> EPL_DEVICE void accumulate8(float (&acc)[8], const int4& raw);
+template <> EPL_DEVICE void accumulate8<__nv_bfloat16>(float (&acc)[8], const int4& raw) {
+  const uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = unpack_bf16x2(w[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+}
+template <> EPL_DEVICE void accumulate8<__half>(float (&acc)[8], const int4& raw) {
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+}
+
+EPL_DEVICE int4 ld_peer(const void* p) {          // peer memory: bypass L1 allocation, data is read once
+  int4 r;
+  asm volatile("ld.global.relaxed.sys.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+EPL_DEVICE void st_peer(void* p, const int4& v) {
+  asm volatile("st.global.relaxed.sys.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// G = gradient / weight element type (bf16 or fp16), 8 elements (16 bytes) per thread per iteration
+template <typename G, bool kHasMask>
+__global__ void __launch_bounds__(512, 1) fused_rs_adam_ag_kernel(const FusedDpArgs a) {
+  barrier_start(a);
+  const int64_t nvec = a.shard_n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const int64_t e = a.shard_start + (i << 3);            // element offset inside the bucket
+    // ---- reduce-scatter: W peer loads in flight, starting with a different peer on every rank -----------------
+    int4 raw[kMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p < a.world) {
+        const int src = (a.rank + p) % a.world;
+        raw[p] = ld_peer(reinterpret_cast<const G*>(a.grads.ptr[src]) + e);
+      }
+    }
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) if (p < a.world) accumulate8<G>(g, raw[p]);
+    // ---- AdamW on the fp32 shard ------------------------------------------------------------------------------
+    float4 p0 = reinterpret_cast<const float4*>(a.master)[2 * i], p1 = reinterpret_cast<const float4*>(a.master)[2 * i + 1];
+    float4 m0 = reinterpret_cast<const float4*>(a.m)[2 * i], m1 = reinterpret_cast<const float4*>(a.m)[2 * i + 1];
+    float4 v0 = reinterpret_cast<const float4*>(a.v)[2 * i], v1 = reinterpret_cast<const float4*>(a.v)[2 * i + 1];
+    float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float kk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if constexpr (kHasMask) {
+      float4 k0 = reinterpret_cast<const float4*>(a.mask)[2 * i], k1 = reinterpret_cast<const float4*>(a.mask)[2 * i + 1];
+      kk[0] = k0.x; kk[1] = k0.y; kk[2] = k0.z; kk[3] = k0.w; kk[4] = k1.x; kk[5] = k1.y; kk[6] = k1.z; kk[7] = k1.w;
+    }
+    uint32_t packed[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gr = g[j] * a.grad_scale;
+      mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * gr;
+      vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * gr * gr;
+      pp[j] -= a.lr * ((mm[j] * a.inv_c1) / (sqrtf(vv[j] * a.inv_c2) + a.eps) + a.weight_decay * kk[j] * pp[j]);
+    }
+    reinterpret_cast<float4*>(a.master)[2 * i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(a.master)[2 * i + 1] = make_float4(pp[4], pp[5], pp[6], pp[7]);
+    reinterpret_cast<float4*>(a.m)[2 * i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(a.m)[2 * i + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
+    reinterpret_cast<float4*>(a.v)[2 * i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(a.v)[2 * i + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    if constexpr (sizeof(G) == 2 && std::is_same<G, __nv_bfloat16>::value) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) packed[j] = pack_bf16x2(pp[2 * j], pp[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { __half2 h = __floats2half2_rn(pp[2 * j], pp[2 * j + 1]); packed[j] = *reinterpret_cast<uint32_t*>(&h); }
+    }
+    const int4 w = make_int4((int)packed[0], (int)packed[1], (int)packed[2], (int)packed[3]);
+    // ---- all-gather: push the new weights into every rank's parameter buffer -------------------------------------
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p < a.world) {
+        const int dst = (a.rank + p) % a.world;
+        st_peer(reinterpret_cast<G*>(a.params.ptr[dst]) + e, w);
+      }
+    }
+  }
+  barrier_end(a);
+}
+
+// Stand-alone device barrier over the same flag protocol (used by tests and by the Python engine between phases)
+__global__ void symm_barrier_kernel(PeerTable flags, int rank, int world, uint32_t epoch) {
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    uint32_t* peer = reinterpret_cast<uint32_t*>(flags.ptr[threadIdx.x]);
+    st_release_sys(peer + rank, epoch);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.ptr[rank]);
+    while (ld_acquire_sys(mine + threadIdx.x) < epoch) {}
+  }
+}
+
+// peer-copy bandwidth probe: dst (local) <- src (peer), 16-byte vectors
+__global__ void __launch_bounds__(512) peer_copy_kernel(const int4* __restrict__ src, int4* __restrict__ dst, int64_t nvec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) dst[i] = ld_peer(src + i);
+}
+
+}  // namespace epl
+using namespace epl;
+
+extern "C" {
+
+int epl_symm_alloc(int64_t bytes, void** out) {
+  cudaError_t e = cudaMalloc(out, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemset(*out, 0, (size_t)bytes);
+}
+int epl_symm_free(void* p) { return (int)cudaFree(p); }
+int epl_symm_export(void* p, void* handle64) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+int epl_symm_import(const void* handle64, void** out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int epl_symm_unimport(void* p) { return (int)cudaIpcCloseMemHandle(p); }
+
+int epl_symm_barrier(void* const* flag_ptrs, int rank, int world, unsigned epoch, void* stream) {
+  PeerTable t;
+  for (int i = 0; i < kMaxPeers; ++i) t.ptr[i] = i < world ? flag_ptrs[i] : nullptr;
+  symm_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, rank, world, epoch);
+  return EPL_CHECK_LAUNCH();
+}
+
+int epl_peer_copy(const void* src, void* dst, int64_t bytes, int blocks, void* stream) {
+  peer_copy_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>((const int4*)src, (int4*)dst, bytes / 16);
+  return EPL_CHECK_LAUNCH();
+}
+
+// grad/param element dtype: EPL_BF16 or EPL_F16.  shard_n must be a multiple of 8, shard_start too.
+int epl_fused_rs_adam_ag(void* const* grad_ptrs, void* const* param_ptrs, void* const* flag_ptrs, void* local_sync,
+                         void* master, void* m, void* v, const void* mask, int64_t shard_start, int64_t shard_n,
+                         int rank, int world, unsigned epoch, int dtype, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, float grad_scale, float inv_c1, float inv_c2, int blocks, void* stream) {
+  if (world > kMaxPeers || (shard_n & 7) || (shard_start & 7)) return -20;
+  FusedDpArgs a;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    a.grads.ptr[i] = i < world ? grad_ptrs[i] : nullptr;
+    a.params.ptr[i] = i < world ? param_ptrs[i] : nullptr;
+    a.flags.ptr[i] = i < world ? flag_ptrs[i] : nullptr;
+  }
+  a.local_sync = (uint32_t*)local_sync;
+  a.master = (float*)master; a.m = (float*)m; a.v = (float*)v; a.mask = (const float*)mask;
+  a.shard_start = shard_start; a.shard_n = shard_n; a.rank = rank; a.world = world; a.epoch = epoch;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
+  a.inv_c1 = inv_c1; a.inv_c2 = inv_c2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (blocks <= 0) blocks = kNumSMs;
+  blocks = std::min(blocks, kNumSMs);            // every CTA must be co-resident: the grid spins on a flag
+  if (dtype == EPL_BF16) {
+    if (mask) fused_rs_adam_ag_kernel<__nv_bfloat16, true><<<blocks, 512, 0, st>>>(a);
+    else fused_rs_adam_ag_kernel<__nv_bfloat16, false><<<blocks, 512, 0, st>>>(a);
+  } else if (dtype == EPL_F16) {
+    if (mask) fused_rs_adam_ag_kernel<__half, true><<<blocks, 512, 0, st>>>(a);
+    else fused_rs_adam_ag_kernel<__half, false><<<blocks, 512, 0, st>>>(a);
+  } else {
+    return -1;
+  }
+  return EPL_CHECK_LAUNCH();
+}
+
+}  // extern "C"

@@ -39,6 +39,9 @@ class Env(object):
           pass
     self.__init__()
     self.strategy_context = StrategyContext()
+    from easyparallellibrary_b200.communicators import backend, collective_communicator
+    backend.reset_groups()
+    collective_communicator._REGISTRY.clear()
 
   def init(self, config=None) -> None:
     from easyparallellibrary_b200.ir import capture

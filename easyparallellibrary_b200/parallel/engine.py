@@ -166,11 +166,21 @@ class Trainer(object):
     self.flats: Dict[int, FlatParameters] = {}
     self.optimizers: Dict[int, List[FlatOptimizer]] = {}
     zero = cfg.zero.level
+    # process groups are created collectively and in the same order on every rank
+    from easyparallellibrary_b200.communicators.backend import register_groups
+    dp_groups = []
+    for reps in self.plan.stage_ranks:
+      for slot in range(len(reps[0])):
+        ranks = [devs[slot] for devs in reps]
+        if ranks not in dp_groups:
+          dp_groups.append(ranks)
+    register_groups(dp_groups, copies=cfg.communication.num_communicators)
     for s in self.plan.local_stages:
       tg_index = self.plan.stage_taskgraphs[s]
       pl = self.plan.placements[tg_index]
       comm = CollectiveCommunicator("DATA_PARALLEL_GRADS_REDUCE_%d" % s, pl.dp_ranks, device=self.device)
       self.dp_comms[s] = comm
+      self._cur_stage = s
       seen, params = set(), []
       for p in self.stage_modules[s].parameters():
         if id(p) not in seen and p.requires_grad and not getattr(p, "epl_tp_sharded_grad_skip", False):
@@ -210,7 +220,26 @@ class Trainer(object):
     return self
 
   def _bucket_allocator(self, comm):
-    return None
+    """Flat weight / gradient buffers live in NVLink symmetric memory when the fused data-parallel kernel
+    will run (same allocation order on every rank, so the buffers pair up)."""
+    from easyparallellibrary_b200.parallel.fused_dp import FusedDataParallel
+    if not FusedDataParallel.eligible(self, comm):
+      return None
+    from easyparallellibrary_b200.runtime.symmetric import SymmetricBuffer
+    if not hasattr(self, "_symm_buffers"):
+      self._symm_buffers = {}
+    stage = len(self.dp_comms) - 1
+    state = {"n": 0}
+
+    def alloc(numel, dtype, device):
+      kind = "param" if state["n"] % 2 == 0 else "grad"
+      state["n"] += 1
+      if dtype not in (torch.bfloat16, torch.float16):
+        return torch.zeros(numel, dtype=dtype, device=device)
+      buf = SymmetricBuffer(numel * 2, comm.ranks, device)
+      self._symm_buffers[(self._cur_stage, kind, dtype)] = buf
+      return buf.tensor(dtype, numel)
+    return alloc
 
   def _setup_fused(self, cfg) -> None:
     """Fused reduce-scatter + Adam + all-gather over NVLink peer memory (K1)."""
@@ -390,7 +419,11 @@ class Trainer(object):
     local_coef = 1.0
     if self.max_grad_norm is not None and not clip_after:
       gnorm = self._grad_norm(reduced=False) * inv
-      local_coef = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
+      c = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
+      if c < 1.0:                       # each replica clips its own gradient, then the clipped ones are reduced
+        for s_ in self.plan.local_stages:
+          for g_ in self.flats[s_].flat_grads.values():
+            g_.mul_(c)
     # (2) reduce, last bucket first (its gradients were produced first)
     launched = {(s, b.index) for s, b, _ in self._pending}
     for s in self.plan.local_stages:

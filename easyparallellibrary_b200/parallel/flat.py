@@ -52,6 +52,9 @@ class FlatParameters(object):
     self.params = params
     self.shard_world = max(int(shard_world), 1)
     self.buckets: List[Bucket] = []
+    self.flat_params: Dict[torch.dtype, torch.Tensor] = {}
+    self.flat_grads: Dict[torch.dtype, torch.Tensor] = {}
+    self.grad_dtype = grad_dtype
     if not params:
       return
     device = params[0].device
@@ -70,8 +73,6 @@ class FlatParameters(object):
       start = per_dtype_off.get(dt, 0)
       per_dtype_off[dt] = start + numel
       layout.append((bi, dt, start, numel, [params[i] for i in idxs], offsets))
-    self.flat_params: Dict[torch.dtype, torch.Tensor] = {}
-    self.flat_grads: Dict[torch.dtype, torch.Tensor] = {}
     for dt, total in per_dtype_off.items():
       self.flat_params[dt] = alloc(total, dt, device)
       self.flat_grads[dt] = alloc(total, grad_dtype or dt, device)

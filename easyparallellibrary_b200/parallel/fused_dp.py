@@ -1,0 +1,81 @@
+"""Data-parallel hot path on B200: fused reduce-scatter + AdamW + all-gather over NVLink peer memory.
+
+One kernel launch per gradient bucket (``csrc/symm.cu: fused_rs_adam_ag_kernel``) replaces
+``ncclAllReduce`` + divide + unfused optimizer (reference ``graph_editor.py:670-725``,
+``adam_weight_decay_optimizer.py:117-153``).  Optimizer state is an equal flat shard per rank, i.e.
+ZeRO-v1 memory falls out for free; weights and gradients live in symmetric memory so the kernel
+reads peers' gradient shards and writes peers' weight shards directly.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from easyparallellibrary_b200.ops import _lib
+from easyparallellibrary_b200.runtime.symmetric import SignalPad, SymmetricBuffer, _sym_lib
+
+
+class FusedDataParallel(object):
+  @staticmethod
+  def eligible(trainer, comm) -> bool:
+    cfg = trainer.config
+    return (trainer.device.type == "cuda" and not trainer.baseline and cfg.communication.fused_kernels
+            and 1 < comm.size <= 8 and trainer.max_grad_norm is None and cfg.offload.level == ""
+            and cfg.zero.level in ("", "v0", "v1") and trainer.opt_kind in ("adam", "adamw")
+            and cfg.optimizer.num_apply_group == 1
+            and trainer.compute_dtype in (torch.bfloat16, torch.float16) and not isinstance(
+                trainer.scaler, __import__("easyparallellibrary_b200.runtime.amp", fromlist=["DynamicLossScale"]).DynamicLossScale))
+
+  def __init__(self, trainer):
+    self.trainer = trainer
+    self.lib = _sym_lib()
+    self.pads: Dict[int, SignalPad] = {}
+    self.local_sync: Dict[int, torch.Tensor] = {}
+    self.epochs: Dict[Tuple[int, int], int] = {}
+    self.side = torch.cuda.Stream(device=trainer.device, priority=-1)
+    self.blocks = 148
+
+  @classmethod
+  def maybe_create(cls, trainer) -> Optional["FusedDataParallel"]:
+    if not getattr(trainer, "_symm_buffers", None):
+      return None
+    self = cls(trainer)
+    for s in trainer.plan.local_stages:
+      comm = trainer.dp_comms[s]
+      flat = trainer.flats[s]
+      self.pads[s] = SignalPad(len(flat.buckets), comm.ranks, trainer.device)
+      self.local_sync[s] = torch.zeros(2 * len(flat.buckets), dtype=torch.int32, device=trainer.device)
+    return self
+
+  def launch_bucket(self, s: int, bi: int, mean: bool) -> None:
+    tr = self.trainer
+    comm, flat = tr.dp_comms[s], tr.flats[s]
+    b, opt = flat.buckets[bi], tr.optimizers[s][bi]
+    gbuf, pbuf = tr._symm_buffers[(s, "grad", b.dtype)], tr._symm_buffers[(s, "param", b.dtype)]
+    es = b.flat_grad.element_size()
+    lo, hi = b.shard_range(comm.rank, comm.size)
+    key = (s, bi)
+    self.epochs[key] = self.epochs.get(key, 0) + 1
+    opt.step_count += 1
+    h = opt.hyper
+    if h.bias_correction:
+      inv_c1, inv_c2 = 1.0 / (1.0 - h.beta1 ** opt.step_count), 1.0 / (1.0 - h.beta2 ** opt.step_count)
+    else:
+      inv_c1 = inv_c2 = 1.0
+    scale = tr.scaler.inv_scale / (comm.size if mean else 1)
+    sync = self.local_sync[s][2 * bi:2 * bi + 2]
+    rc = self.lib.epl_fused_rs_adam_ag(
+        gbuf.peer_table(b.start * es), pbuf.peer_table(b.start * es), self.pads[s].slot_table(bi), sync.data_ptr(),
+        opt.master.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), _lib.ptr(opt.decay_mask), lo, hi - lo, comm.rank,
+        comm.size, self.epochs[key], _lib.dtype_code(b.dtype), h.lr, h.beta1, h.beta2, h.eps, h.weight_decay, scale,
+        inv_c1, inv_c2, self.blocks, _lib.stream())
+    _lib.check(rc, "fused_rs_adam_ag")
+
+  def reduce_and_apply(self, mean: bool):
+    tr = self.trainer
+    for s in tr.plan.local_stages:
+      for bi in range(len(tr.flats[s].buckets) - 1, -1, -1):
+        self.launch_bucket(s, bi, mean)
+    return False, None

@@ -88,11 +88,14 @@ def build_stage_program(policy: str, stage: int, num_stages: int, num_micro_batc
     slots.append([pre, ins, post])
   prog: List[Instr] = []
   posted = set()
+  f_slot = {ins.mb: n for n, (_, ins, _) in enumerate(slots) if ins.op == F}
   for i, (pre, ins, post) in enumerate(slots):
-    # post this slot's receives (if not already) plus those of the next `prefetch` slots that receive anything
+    # post this slot's receives (if not already) plus those of the next `prefetch` slots that receive anything;
+    # a gradient receive is never hoisted above the forward of its own micro-batch (its buffer mirrors that output)
     ahead, j = 0, i
     while j < len(slots) and ahead <= max(prefetch, 0):
-      if slots[j][0] or j == i:
+      hoistable = j == i or slots[j][1].op == F or f_slot[slots[j][1].mb] < i
+      if (slots[j][0] and hoistable) or j == i:
         for r in slots[j][0]:
           if (r.op, r.mb) not in posted:
             posted.add((r.op, r.mb))

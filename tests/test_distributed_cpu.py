@@ -1,0 +1,224 @@
+"""Multi-process CPU (gloo) tests: communicator verbs, DP/ZeRO/GA parity, pipeline parity, collections.
+The reference has no CPU communication backend and only two true multi-process tests;
+this tier is what BASELINE config #1 asks for."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from dist_utils import run_distributed
+
+
+# ------------------------------------------------------------------------------------------- communicator
+def _comm_worker(rank, world):
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.communicators import CollectiveCommunicator
+  from easyparallellibrary_b200.communicators import functional as F
+  from easyparallellibrary_b200.communicators.sparse import sparse_all_reduce
+  epl.init()
+  comm = CollectiveCommunicator("test", list(range(world)), max_splits=3, num_communicators=2)
+  out = {}
+  ts = [torch.full((n,), float(rank + 1)) for n in (3, 5, 7, 11)] + [torch.full((4,), rank + 1, dtype=torch.int64)]
+  red = comm.batch_allreduce(ts, mean=False)
+  out["allreduce"] = [t.tolist() for t in red]
+  out["mean"] = comm.batch_allreduce([torch.full((2,), float(rank))], mean=True)[0].tolist()
+  comm16 = CollectiveCommunicator("test16", list(range(world)), enable_fp16=True, fp16_scale=128)
+  out["fp16"] = comm16.batch_allreduce([torch.full((4,), 0.5 * (rank + 1))], mean=False)[0].tolist()
+  b = torch.full((6,), float(rank))
+  comm.broadcast(b, root=1)
+  out["broadcast"] = b.tolist()
+  out["allgather"] = comm.allgather(torch.full((2, 2), float(rank))).tolist()
+  out["reduce"] = comm.reduce(torch.ones(3) * (rank + 1), root=0).tolist()
+  out["reduce_scatter"] = comm.reduce_scatter(torch.arange(2 * world, dtype=torch.float32) * (rank + 1)).tolist()
+  out["alltoall"] = comm.alltoall(torch.arange(world * 2, dtype=torch.float32) + 100 * rank).tolist()
+  g, counts = comm.allgatherv(torch.full((rank + 1, 2), float(rank)))
+  out["allgatherv"] = (g.tolist(), counts.tolist())
+  rows = torch.arange(3, dtype=torch.float32).unsqueeze(1) + 10 * rank          # 3 rows: send 1 to rank0, 2 to rank1
+  recv, rc = comm.alltoallv(rows, torch.tensor([1, 2]))
+  out["alltoallv"] = (recv.flatten().tolist(), rc.tolist())
+  # autograd adjoints
+  x = torch.ones(2, 3, requires_grad=True)
+  F.all_gather(x * (rank + 1), comm).sum().backward()
+  out["ag_grad"] = x.grad.tolist()
+  y = torch.ones(2 * world, requires_grad=True)
+  (F.reduce_scatter(y, comm) * (rank + 1)).sum().backward()
+  out["rs_grad"] = y.grad.tolist()
+  z = torch.ones(4, requires_grad=True)
+  F.all_reduce(z * 2, comm).sum().backward()
+  out["ar_grad"] = z.grad.tolist()
+  w = torch.arange(2.0 * world, requires_grad=True)
+  (F.all_to_all(w, comm) * (rank + 1)).sum().backward()
+  out["a2a_grad"] = w.grad.tolist()
+  sp = torch.sparse_coo_tensor(torch.tensor([[rank, 3]]), torch.ones(2, 2) * (rank + 1), (5, 2))
+  out["sparse"] = sparse_all_reduce(comm, sp).to_dense().tolist()
+  return out
+
+
+def test_communicator_verbs_two_ranks():
+  r0, r1 = run_distributed(_comm_worker, 2)
+  assert r0["allreduce"] == [[3.0] * 3, [3.0] * 5, [3.0] * 7, [3.0] * 11, [3] * 4] == r1["allreduce"]
+  assert r0["mean"] == [0.5, 0.5]
+  assert r0["fp16"] == [1.5] * 4
+  assert r0["broadcast"] == [1.0] * 6 == r1["broadcast"]
+  assert r0["allgather"] == [[0.0, 0.0], [0.0, 0.0], [1.0, 1.0], [1.0, 1.0]]
+  assert r0["reduce"] == [3.0, 3.0, 3.0]
+  assert r0["reduce_scatter"] == [0.0, 3.0] and r1["reduce_scatter"] == [6.0, 9.0]
+  assert r0["alltoall"] == [0.0, 1.0, 100.0, 101.0] and r1["alltoall"] == [2.0, 3.0, 102.0, 103.0]
+  assert r0["allgatherv"][0] == [[0.0, 0.0], [1.0, 1.0], [1.0, 1.0]] and r0["allgatherv"][1] == [1, 2]
+  assert r0["alltoallv"] == ([0.0, 10.0], [1, 1]) and r1["alltoallv"] == ([1.0, 2.0, 11.0, 12.0], [2, 2])
+  assert r0["ag_grad"] == [[2.0] * 3] * 2 and r1["ag_grad"] == [[4.0] * 3] * 2       # adjoint = reduce-scatter
+  assert r0["rs_grad"] == [1.0, 1.0, 2.0, 2.0]                                        # adjoint = all-gather
+  assert r0["ar_grad"] == [4.0] * 4
+  assert r0["a2a_grad"] == [1.0, 1.0, 2.0, 2.0]
+  assert r0["sparse"] == [[1.0, 1.0], [2.0, 2.0], [0.0, 0.0], [3.0, 3.0], [0.0, 0.0]]
+
+
+# ------------------------------------------------------------------------------------------- DP parity
+def _mlp():
+  torch.manual_seed(0)
+  return nn.Sequential(nn.Linear(10, 16), nn.ReLU(), nn.Linear(16, 1))
+
+
+def _train(rank, world, conf, steps=4, clip=None, opt="adamw"):
+  import easyparallellibrary_b200 as epl
+  epl.init(epl.Config(conf))
+  with epl.replicate(device_count=1):
+    model = _mlp()
+  tr = epl.Trainer(model, opt, loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2, max_grad_norm=clip)
+  torch.manual_seed(1)
+  X, Y = torch.randn(steps, 8, 10), torch.randn(steps, 8, 1)
+  losses = []
+  for i in range(steps):
+    x, y = X[i], Y[i]
+    if tr.build().plan.num_replicas > 1:
+      n = tr.plan.num_replicas
+      r = tr.plan.placements[tr.plan.stage_taskgraphs[0]].replica
+      x, y = x.chunk(n)[r], y.chunk(n)[r]
+    out = tr.step(x, y)
+    epl.add_to_collection  # noqa: B018
+    losses.append(out.item())
+  return losses, [p.detach().float().numpy().copy() for p in model.parameters()]
+
+
+def _max_diff(a, b):
+  return max(float(np.abs(x - y).max()) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("conf", [
+    {}, {"zero.level": "v0"}, {"zero.level": "v1"}, {"communication.fp16": True, "communication.fp16_scale": 64},
+    {"pipeline.num_micro_batch": 2}, {"optimizer.num_apply_group": 3}, {"communication.max_splits": 1},
+])
+def test_data_parallel_matches_single_process(conf):
+  base = run_distributed(_train, 1, args=({k: v for k, v in conf.items() if k.startswith(("pipeline", "optimizer"))},))[0]
+  dist_res = run_distributed(_train, 2, args=(conf,))
+  tol = 2e-3 if conf.get("communication.fp16") else 1e-6
+  for res in dist_res:
+    assert _max_diff(base[1], res[1]) < tol
+  assert _max_diff(dist_res[0][1], dist_res[1][1]) == 0.0       # replicas stay bit-identical
+
+
+def test_sgd_and_clipping_modes():
+  for conf in ({}, {"communication.clip_after_allreduce": True}):
+    base = run_distributed(_train, 1, args=({}, 3, 0.5, "sgd"))[0]
+    two = run_distributed(_train, 2, args=(conf, 3, 0.5, "sgd"))
+    if conf:      # reduce-then-clip == single process on the full batch
+      assert _max_diff(base[1], two[0][1]) < 1e-6
+    assert _max_diff(two[0][1], two[1][1]) < 1e-7
+
+
+def test_gradient_accumulation_equals_big_batch():
+  a = run_distributed(_train, 1, args=({},))[0]
+  b = run_distributed(_train, 1, args=({"pipeline.num_micro_batch": 4},))[0]
+  assert _max_diff(a[1], b[1]) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- pipeline parity
+_LAYER_FACTORIES = [lambda: nn.Sequential(nn.Linear(10, 32), nn.Tanh()), lambda: nn.Sequential(nn.Linear(32, 32), nn.Tanh()),
+                    lambda: nn.Sequential(nn.Linear(32, 32), nn.Tanh()), lambda: nn.Linear(32, 1)]
+
+
+def _train_pipe(rank, world, conf, stages, steps=3):
+  import easyparallellibrary_b200 as epl
+  epl.init(epl.Config(conf))
+  torch.manual_seed(0)
+  per = len(_LAYER_FACTORIES) // stages
+  mods = []
+  for s in range(stages):
+    with epl.replicate(device_count=1, name="stage%d" % s):
+      mods.append(nn.Sequential(*[f() for f in _LAYER_FACTORIES[s * per:(s + 1) * per]]))
+  model = nn.Sequential(*mods)
+  tr = epl.Trainer(model, "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2).build()
+  torch.manual_seed(1)
+  X, Y = torch.randn(steps, 16, 10), torch.randn(steps, 16, 1)
+  n = tr.plan.num_replicas
+  rep = next(iter(tr.plan.placements.values())).replica
+  losses = []
+  for i in range(steps):
+    x, y = X[i].chunk(n)[rep], Y[i].chunk(n)[rep]
+    losses.append(tr.step(x, y).item())
+  params = {}
+  for s in tr.plan.local_stages:
+    for k, v in tr.stage_modules[s].state_dict().items():
+      params["%d.%s" % (s, k)] = v.float().numpy().copy()
+  return losses, params, tr.plan.pipeline
+
+
+@pytest.mark.parametrize("policy", ["PreferBackward", "PreferForward", "PreferBackwardOptimizer"])
+def test_two_stage_pipeline_matches_single_process(policy):
+  conf = {"pipeline.num_micro_batch": 4, "pipeline.strategy": policy}
+  base = run_distributed(_train_pipe, 1, args=(conf, 2))[0]
+  res = run_distributed(_train_pipe, 2, args=(conf, 2))
+  assert res[0][2] and res[1][2] and not base[2]
+  merged = {}
+  for r in res:
+    merged.update(r[1])
+  assert set(merged) == set(base[1])
+  assert max(float(np.abs(merged[k] - base[1][k]).max()) for k in merged) < 1e-6
+  for a, b in zip(res[0][0], base[0]):
+    assert abs(a - b) < 1e-5          # every stage reports the replica's loss
+
+
+def test_pipeline_times_data_parallel_four_ranks():
+  conf = {"pipeline.num_micro_batch": 2}
+  base = run_distributed(_train_pipe, 1, args=(conf, 2))[0]
+  res = run_distributed(_train_pipe, 4, args=(conf, 2))
+  merged = {}
+  for r in res:
+    merged.update(r[1])
+  assert max(float(np.abs(merged[k] - base[1][k]).max()) for k in merged) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- collections
+def _collections_worker(rank, world):
+  import easyparallellibrary_b200 as epl
+  epl.init(epl.Config({"pipeline.num_micro_batch": 2}))
+
+  class Net(nn.Module):
+    def __init__(self):
+      super().__init__()
+      self.fc = nn.Linear(4, 1)
+
+    def forward(self, x, y):
+      out = self.fc(x)
+      loss = ((out - y) ** 2).mean()
+      epl.add_to_collection(loss, epl.GraphKeys.GLOBAL_MEAN_OBJECTS)
+      epl.add_to_collection(out.detach().flatten(), epl.GraphKeys.GLOBAL_CONCAT_OBJECTS)
+      epl.add_to_collection(torch.tensor(float(x.shape[0])), epl.GraphKeys.GLOBAL_SUM_OBJECTS)
+      epl.add_to_collection(torch.tensor(float(rank)), epl.GraphKeys.LOCAL_MEAN_OBJECTS)
+      return loss
+
+  with epl.replicate(1):
+    net = Net()
+  tr = epl.Trainer(net, "sgd", lr=0.0)
+  x, y = torch.ones(4, 4) * (rank + 1), torch.zeros(4, 1)
+  out = tr.step(x, y)
+  c = out.collections
+  return {k: [v.tolist() if v.dim() else float(v) for v in vals] for k, vals in c.items()}
+
+
+def test_collections_merge_over_micro_batches_and_replicas():
+  r0, r1 = run_distributed(_collections_worker, 2)
+  assert r0[r"global_sum_objects"] == [8.0]                    # 2 micro-batches x 2 rows x 2 replicas
+  assert len(r0["global_concat_objects"][0]) == 8
+  assert r0["global_mean_objects"] == r1["global_mean_objects"]
+  assert r0["local_mean_objects"] == [0.0] and r1["local_mean_objects"] == [1.0]

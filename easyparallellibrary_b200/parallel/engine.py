@@ -236,7 +236,7 @@ class Trainer(object):
       state["n"] += 1
       if dtype not in (torch.bfloat16, torch.float16):
         return torch.zeros(numel, dtype=dtype, device=device)
-      buf = SymmetricBuffer(numel * 2, comm.ranks, device)
+      buf = SymmetricBuffer(numel * 2, comm.ranks, device, group=getattr(comm.primary, "group", None))
       self._symm_buffers[(self._cur_stage, kind, dtype)] = buf
       return buf.tensor(dtype, numel)
     return alloc

@@ -45,7 +45,7 @@ class FusedDataParallel(object):
     for s in trainer.plan.local_stages:
       comm = trainer.dp_comms[s]
       flat = trainer.flats[s]
-      self.pads[s] = SignalPad(len(flat.buckets), comm.ranks, trainer.device)
+      self.pads[s] = SignalPad(len(flat.buckets), comm.ranks, trainer.device, group=getattr(comm.primary, "group", None))
       self.local_sync[s] = torch.zeros(2 * len(flat.buckets), dtype=torch.int32, device=trainer.device)
     return self
 

@@ -60,28 +60,32 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ pre
   }
 }
 
-// column sums: out[d] (+)= sum_r x[r][d].  grid = (ceil(D/64), row_chunks); partial sums via atomicAdd on fp32 scratch.
+// column sums: scratch[d] += sum_r x[r][d].  Block (32, 8): thread x owns 16 bytes of consecutive columns, rows are
+// strided over threadIdx.y and blockIdx.y; per-CTA smem reduction, one fp32 atomicAdd per column per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ scratch, int rows, int D) {
-  // block: 64 columns x 4 row-lanes; 2 columns per thread in x (bf16x2) -> threads.x = 32, threads.y = 8
-  const int col = (blockIdx.x * 32 + threadIdx.x) * 2;
-  float a0 = 0.f, a1 = 0.f;
+  constexpr int E = 16 / sizeof(T);
+  const int col = (blockIdx.x * 32 + threadIdx.x) * E;
+  float acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
   if (col < D) {
-    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < rows; r += gridDim.y * blockDim.y) {
-      const T* p = x + (size_t)r * D + col;
-      a0 += to_f32<T>(p[0]);
-      if (col + 1 < D) a1 += to_f32<T>(p[1]);
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < rows; r += gridDim.y * 8) {
+      Vec<T, E> v = ld_vec<T, E>(x + (size_t)r * D + col);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] += to_f32<T>(v.v[e]);
     }
   }
-  __shared__ float s[8][64];
-  s[threadIdx.y][threadIdx.x * 2] = a0;
-  s[threadIdx.y][threadIdx.x * 2 + 1] = a1;
-  __syncthreads();
-  if (threadIdx.y == 0) {
+  __shared__ float s[8][32 * E + 1];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { a0 += s[k][threadIdx.x * 2]; a1 += s[k][threadIdx.x * 2 + 1]; }
-    if (col < D) atomicAdd(&scratch[col], a0);
-    if (col + 1 < D) atomicAdd(&scratch[col + 1], a1);
+  for (int e = 0; e < E; ++e) s[threadIdx.y][threadIdx.x * E + e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.y * 32 + threadIdx.x; c < 32 * E; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][c];
+    const int gc = blockIdx.x * 32 * E + c;
+    if (gc < D) atomicAdd(&scratch[gc], t);
   }
 }
 
@@ -144,8 +148,10 @@ extern "C" int epl_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t
 extern "C" int epl_colsum(const void* x, void* out, void* scratch, int rows, int D, int dtype, int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(scratch, 0, (size_t)D * sizeof(float), st);
-  dim3 block(32, 8), grid((D + 63) / 64, std::max(1, std::min((rows + 63) / 64, 64)));
   BY_DTYPE(dtype, {
+    constexpr int E = 16 / sizeof(T);
+    const int gx = (D + 32 * E - 1) / (32 * E);
+    dim3 block(32, 8), grid(gx, std::max(1, std::min((rows + 31) / 32, (2 * kNumSMs + gx - 1) / gx)));
     colsum_kernel<T><<<grid, block, 0, st>>>((const T*)x, (float*)scratch, rows, D);
     finish_colsum_kernel<T><<<(D + 255) / 256, 256, 0, st>>>((const float*)scratch, (T*)out, D, accumulate);
   });

@@ -84,7 +84,8 @@ template <typename T, int VPT, bool kRms>
 __global__ void __launch_bounds__(kBwdThreads)
 norm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ gamma,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dx,
-                float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows, int D) {
+                float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows, int D,
+                const T* __restrict__ dres) {
   constexpr int E = 16 / sizeof(T);
   __shared__ float red[2][2][kBwdThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,8 +141,14 @@ norm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __re
       int vi = threadIdx.x + i * kBwdThreads;
       if (vi < nvec) {
         Vec<T, E> o;
+        if (dres != nullptr) {               // fused residual-branch gradient: dx = LN'(dy) + d(skip)
+          Vec<T, E> rv = ld_vec<T, E>(dres + (size_t)row * D + vi * E);
 #pragma unroll
-        for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>(rstd * (gd[i][e] - s1 - xh[i][e] * s2));
+          for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>(rstd * (gd[i][e] - s1 - xh[i][e] * s2) + to_f32<T>(rv.v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>(rstd * (gd[i][e] - s1 - xh[i][e] * s2));
+        }
         st_vec<T, E>(dxr + vi * E, o);
       }
     }
@@ -159,16 +166,23 @@ norm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __re
   }
 }
 
-// out[d] = sum_p part[p][d]  (accumulate into existing grad when acc != 0)
+// out[d] = sum_p part[p][d]  (accumulate into existing grad when acc != 0).  Block = 32 columns x 16 part-lanes.
 template <typename T>
-__global__ void __launch_bounds__(256) norm_param_reduce_kernel(const float* __restrict__ part, int parts, int D,
+__global__ void __launch_bounds__(512) norm_param_reduce_kernel(const float* __restrict__ part, int parts, int D,
                                                                  T* __restrict__ out, int accumulate) {
-  int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
-  float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += part[(size_t)p * D + d];
-  if (accumulate) s += to_f32<T>(out[d]);
-  out[d] = from_f32<T>(s);
+  __shared__ float s[16][33];
+  const int d = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (d < D)
+    for (int p = threadIdx.y; p < parts; p += 16) acc += part[(size_t)p * D + d];
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && d < D) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) acc += s[k][threadIdx.x];
+    if (accumulate) acc += to_f32<T>(out[d]);
+    out[d] = from_f32<T>(acc);
+  }
 }
 
 template <typename T, bool kRms>
@@ -190,13 +204,13 @@ static int launch_fwd(const void* x, const void* g, const void* b, void* y, floa
 
 template <typename T, bool kRms>
 static int launch_bwd(const void* x, const void* dy, const void* g, const float* mean, const float* rstd, void* dx,
-                      float* pg, float* pb, int grid, int rows, int D, cudaStream_t st) {
+                      float* pg, float* pb, int grid, int rows, int D, const void* dres, cudaStream_t st) {
   constexpr int E = 16 / sizeof(T);
   int nvec = D / E;
   int vpt = (nvec + kBwdThreads - 1) / kBwdThreads;
   const T *xp = (const T*)x, *dp = (const T*)dy, *gp = (const T*)g;
   T* dxp = (T*)dx;
-#define LAUNCH(V) norm_bwd_kernel<T, V, kRms><<<grid, kBwdThreads, 0, st>>>(xp, dp, gp, mean, rstd, dxp, pg, pb, rows, D)
+#define LAUNCH(V) norm_bwd_kernel<T, V, kRms><<<grid, kBwdThreads, 0, st>>>(xp, dp, gp, mean, rstd, dxp, pg, pb, rows, D, (const T*)dres)
   if (vpt <= 1) LAUNCH(1); else if (vpt <= 2) LAUNCH(2); else if (vpt <= 4) LAUNCH(4); else if (vpt <= 8) LAUNCH(8); else return -2;
 #undef LAUNCH
   return EPL_CHECK_LAUNCH();
@@ -224,23 +238,24 @@ extern "C" int epl_norm_bwd_grid(int rows) { return std::min(rows, kNumSMs * 4);
 // workspace: 2 * grid * D floats (grid from epl_norm_bwd_grid)
 extern "C" int epl_norm_bwd(const void* x, const void* dy, const void* gamma, const void* mean, const void* rstd,
                             void* dx, void* dgamma, void* dbeta, void* workspace, int rows, int D, int dtype, int rms,
-                            int accumulate, void* stream) {
+                            int accumulate, const void* dres, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (rows <= 0) return 0;
   int grid = epl_norm_bwd_grid(rows);
   float* pg = (float*)workspace;
   float* pb = rms ? nullptr : pg + (size_t)grid * D;
   int rc;
-#define GO(T) (rms ? launch_bwd<T, true>(x, dy, gamma, nullptr, (const float*)rstd, dx, pg, pb, grid, rows, D, st)  \
-                   : launch_bwd<T, false>(x, dy, gamma, (const float*)mean, (const float*)rstd, dx, pg, pb, grid, rows, D, st))
+#define GO(T) (rms ? launch_bwd<T, true>(x, dy, gamma, nullptr, (const float*)rstd, dx, pg, pb, grid, rows, D, dres, st)  \
+                   : launch_bwd<T, false>(x, dy, gamma, (const float*)mean, (const float*)rstd, dx, pg, pb, grid, rows, D, dres, st))
   if (dtype == EPL_F32) rc = GO(float); else if (dtype == EPL_BF16) rc = GO(__nv_bfloat16); else rc = GO(__half);
 #undef GO
   if (rc) return rc;
-  int rb = (D + 255) / 256;
+  int rb = (D + 31) / 32;
+  dim3 rblock(32, 16);
 #define RED(T)                                                                                                     \
   do {                                                                                                             \
-    norm_param_reduce_kernel<T><<<rb, 256, 0, st>>>(pg, grid, D, (T*)dgamma, accumulate);                          \
-    if (pb) norm_param_reduce_kernel<T><<<rb, 256, 0, st>>>(pb, grid, D, (T*)dbeta, accumulate);                   \
+    norm_param_reduce_kernel<T><<<rb, rblock, 0, st>>>(pg, grid, D, (T*)dgamma, accumulate);                          \
+    if (pb) norm_param_reduce_kernel<T><<<rb, rblock, 0, st>>>(pb, grid, D, (T*)dbeta, accumulate);                   \
   } while (0)
   if (dtype == EPL_F32) RED(float); else if (dtype == EPL_BF16) RED(__nv_bfloat16); else RED(__half);
 #undef RED

@@ -84,12 +84,13 @@ class SelfAttention(nn.Module):
     self.qkv = Linear(d, 3 * d, init_std=0.02)
     self.proj = Linear(d, d, init_std=0.02 / math.sqrt(2 * cfg.n_layer))
 
-  def forward(self, x):
+  def forward(self, x, residual=None):
     B, S, d = x.shape
     qkv = self.qkv(x).view(B, S, 3, self.n_head, d // self.n_head)
     q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)            # [B, H, S, hd] views
     y = attention(q, k, v, causal=True)
-    return self.proj(y.transpose(1, 2).reshape(B, S, d))
+    from easyparallellibrary_b200.ops.linear import linear
+    return linear(y.transpose(1, 2).reshape(B, S, d), self.proj.weight, self.proj.bias, residual=residual)
 
 
 class MLP(nn.Module):
@@ -99,8 +100,8 @@ class MLP(nn.Module):
     self.fc = Linear(d, 4 * d, init_std=0.02)
     self.proj = Linear(4 * d, d, init_std=0.02 / math.sqrt(2 * cfg.n_layer))
 
-  def forward(self, x):
-    return mlp(x, self.fc.weight, self.fc.bias, self.proj.weight, self.proj.bias)
+  def forward(self, x, residual=None):
+    return mlp(x, self.fc.weight, self.fc.bias, self.proj.weight, self.proj.bias, residual)
 
 
 class Block(nn.Module):
@@ -112,8 +113,11 @@ class Block(nn.Module):
     self.mlp = MLP(cfg)
 
   def forward(self, x):
-    x = x + self.attn(self.ln_1(x))
-    return x + self.mlp(self.ln_2(x))
+    # pre-LN residual block; both residual adds run in GEMM epilogues, both gradient joins in the LN backward
+    skip, h = self.ln_1.fork(x)
+    x = self.attn(h, residual=skip)
+    skip, h = self.ln_2.fork(x)
+    return self.mlp(h, residual=skip)
 
 
 class Head(nn.Module):

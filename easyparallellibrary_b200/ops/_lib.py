@@ -59,7 +59,7 @@ class _Sigs:
   epl_sumsq = [_p, _i, _l, _p, _p]
   epl_norm_fwd = [_p, _p, _p, _p, _p, _p, _i, _i, _f, _i, _i, _p]
   epl_norm_bwd_grid = [_i]
-  epl_norm_bwd = [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]
+  epl_norm_bwd = [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]
   epl_bias_gelu_fwd = [_p, _p, _p, _p, _l, _i, _i, _p]
   epl_gelu_bwd = [_p, _p, _p, _l, _i, _p]
   epl_colsum = [_p, _p, _p, _i, _i, _i, _i, _p]

@@ -94,12 +94,18 @@ def _sink_weight_grad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> Opti
 
 class _LinearFn(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, x, w, bias, gelu):
+  def forward(ctx, x, w, bias, gelu, residual=None):
     x2 = x.reshape(-1, x.shape[-1])
     if not x2.is_contiguous():
       x2 = x2.contiguous()
     pre = None
-    if gelu:
+    ctx.has_res = residual is not None
+    if residual is not None:
+      r2 = residual.reshape(-1, w.shape[0])
+      if not r2.is_contiguous():
+        r2 = r2.contiguous()
+      y = gemm(x2, w, bias=bias, epilogue=EPI_BIAS_RESIDUAL, aux=r2)
+    elif gelu:
       pre = torch.empty((x2.shape[0], w.shape[0]), dtype=x.dtype, device=x.device)
       y = gemm(x2, w, bias=bias, epilogue=EPI_BIAS_GELU, pre=pre)
     else:
@@ -123,20 +129,27 @@ class _LinearFn(torch.autograd.Function):
     dx = gemm(dy2, w, b_mn_major=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
     dw = _sink_weight_grad(w, dy2, x2) if ctx.needs_input_grad[1] else None
     db = colsum(dy2) if ctx.has_bias and ctx.needs_input_grad[2] else None
-    return dx, dw, db, None
+    return dx, dw, db, None, (dy if ctx.has_res else None)
 
 
 class _MlpFn(torch.autograd.Function):
   """y = gelu(x W1^T + b1) W2^T + b2, four GEMMs in backward, GELU' fused into the dH epilogue."""
 
   @staticmethod
-  def forward(ctx, x, w1, b1, w2, b2):
+  def forward(ctx, x, w1, b1, w2, b2, residual=None):
     x2 = x.reshape(-1, x.shape[-1])
     if not x2.is_contiguous():
       x2 = x2.contiguous()
     pre = torch.empty((x2.shape[0], w1.shape[0]), dtype=x.dtype, device=x.device)
     h = gemm(x2, w1, bias=b1, epilogue=EPI_BIAS_GELU, pre=pre)
-    y = gemm(h, w2, bias=b2, epilogue=EPI_BIAS if b2 is not None else EPI_NONE)
+    ctx.has_res = residual is not None
+    if residual is not None:
+      r2 = residual.reshape(-1, w2.shape[0])
+      if not r2.is_contiguous():
+        r2 = r2.contiguous()
+      y = gemm(h, w2, bias=b2, epilogue=EPI_BIAS_RESIDUAL, aux=r2)
+    else:
+      y = gemm(h, w2, bias=b2, epilogue=EPI_BIAS if b2 is not None else EPI_NONE)
     ctx.save_for_backward(x2, w1, w2, pre, h)
     ctx.has_b1, ctx.has_b2, ctx.xshape = b1 is not None, b2 is not None, x.shape
     return y.view(*x.shape[:-1], w2.shape[0])
@@ -153,7 +166,7 @@ class _MlpFn(torch.autograd.Function):
     dx = gemm(dpre, w1, b_mn_major=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
     dw1 = _sink_weight_grad(w1, dpre, x2)
     db1 = colsum(dpre) if ctx.has_b1 else None
-    return dx, dw1, db1, dw2, db2
+    return dx, dw1, db1, dw2, db2, (dy if ctx.has_res else None)
 
 
 def _use_kernel(x: torch.Tensor, w: torch.Tensor) -> bool:
@@ -161,18 +174,23 @@ def _use_kernel(x: torch.Tensor, w: torch.Tensor) -> bool:
           and x.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0 and w.is_contiguous())
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False) -> torch.Tensor:
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False,
+           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """``y = x @ w^T (+ bias) (GELU)`` or, with ``residual``, ``y = residual + x @ w^T + bias`` — one kernel either way."""
   if _use_kernel(x, w):
-    return _LinearFn.apply(x, w, bias, gelu)
+    return _LinearFn.apply(x, w, bias, gelu, residual)
   y = torch.nn.functional.linear(x, w, bias)
+  if residual is not None:
+    return residual + y
   return torch.nn.functional.gelu(y, approximate="tanh") if gelu else y
 
 
-def mlp(x, w1, b1, w2, b2) -> torch.Tensor:
+def mlp(x, w1, b1, w2, b2, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
   if _use_kernel(x, w1) and w2.shape[0] % 8 == 0:
-    return _MlpFn.apply(x, w1, b1, w2, b2)
+    return _MlpFn.apply(x, w1, b1, w2, b2, residual)
   h = torch.nn.functional.gelu(torch.nn.functional.linear(x, w1, b1), approximate="tanh")
-  return torch.nn.functional.linear(h, w2, b2)
+  y = torch.nn.functional.linear(h, w2, b2)
+  return y if residual is None else residual + y
 
 
 class Linear(nn.Module):

@@ -322,6 +322,10 @@ class Trainer(object):
         for p, o in zip(b.params, b.offsets):
           self._bucket_of[id(p)] = (s, b, o)
           p.register_post_accumulate_grad_hook(self._on_grad_ready)
+          if p.is_cuda and b.flat_grad.dtype == p.dtype:
+            # weight-gradient GEMMs accumulate straight into the flat bucket (ops/linear.py:_sink_weight_grad)
+            p.epl_main_grad = b.flat_grad[o:o + p.numel()]
+            p.epl_grad_ready = self._on_grad_ready
     self._pending: List[Tuple[int, Bucket, Any]] = []
 
   def _on_grad_ready(self, p: nn.Parameter) -> None:

@@ -88,12 +88,6 @@ class SymmetricBuffer(object):
     t._epl_symm_owner = self          # keep the allocation alive as long as a view exists
     return t
 
-  def peer_tensor(self, peer: int, dtype: torch.dtype, numel: int, byte_offset: int = 0) -> torch.Tensor:
-    nbytes = numel * torch.empty(0, dtype=dtype).element_size()
-    t = wrap_pointer(self.peer_ptrs[peer] + byte_offset, nbytes, dtype, self.device)
-    t._epl_symm_owner = self
-    return t
-
   def peer_table(self, byte_offset: int = 0):
     arr = (ctypes.c_void_p * 8)()
     for r in range(self.world):

@@ -208,3 +208,44 @@ def test_gpt2_tiny_step_matches_torch():
   assert losses[-1] < losses[0]
   for a, b in zip(losses, ref_losses):
     assert abs(a - b) < 0.05 * abs(b) + 0.05, (losses, ref_losses)
+
+
+def test_layernorm_fork_and_residual_linear():
+  """Pre-LN residual block pieces: LN fork (skip gradient joined inside the LN backward kernel) and the
+  residual-add GEMM epilogue, against plain fp32 autograd."""
+  from easyparallellibrary_b200.ops.layernorm import layer_norm_fork
+  from easyparallellibrary_b200.ops.linear import linear, mlp
+  torch.manual_seed(3)
+  B, S, d = 2, 64, 256
+  x = torch.randn(B, S, d, device=DEV).bfloat16().requires_grad_()
+  g = (torch.rand(d, device=DEV) + 0.5).bfloat16().requires_grad_()
+  b = torch.randn(d, device=DEV).bfloat16().requires_grad_()
+  w = (torch.randn(d, d, device=DEV) * 0.05).bfloat16().requires_grad_()
+  wb = torch.randn(d, device=DEV).bfloat16().requires_grad_()
+  w1 = (torch.randn(4 * d, d, device=DEV) * 0.05).bfloat16().requires_grad_()
+  b1 = torch.zeros(4 * d, device=DEV).bfloat16().requires_grad_()
+  w2 = (torch.randn(d, 4 * d, device=DEV) * 0.05).bfloat16().requires_grad_()
+  b2 = torch.zeros(d, device=DEV).bfloat16().requires_grad_()
+  dy = torch.randn(B, S, d, device=DEV).bfloat16()
+
+  def block(x, g, b, w, wb, w1, b1, w2, b2, fused):
+    F = torch.nn.functional
+    if fused:
+      skip, h = layer_norm_fork(x, g, b)
+      x2 = linear(h, w, wb, residual=skip)
+      skip, h = layer_norm_fork(x2, g, b)
+      return mlp(h, w1, b1, w2, b2, residual=skip)
+    h = F.layer_norm(x, (d,), g, b)
+    x2 = x + F.linear(h, w, wb)
+    h = F.layer_norm(x2, (d,), g, b)
+    return x2 + F.linear(F.gelu(F.linear(h, w1, b1), approximate="tanh"), w2, b2)
+
+  params = (x, g, b, w, wb, w1, b1, w2, b2)
+  y = block(*params, True)
+  y.backward(dy)
+  ref = [t.detach().float().requires_grad_() for t in params]
+  yr = block(*ref, False)
+  yr.backward(dy.float())
+  _close(y, yr, 3e-2, 5e-2, "block y")
+  for name, t, r in zip("x g b w wb w1 b1 w2 b2".split(), params, ref):
+    _close(t.grad, r.grad, 4e-2, 4e-2 * r.grad.abs().max().item(), "block d" + name)

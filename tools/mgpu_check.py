@@ -18,9 +18,15 @@ def log(*a):
     print(*a, flush=True)
 
 
+def stage(name):
+  print("[rank %d] %s" % (dist.get_rank(), name), flush=True)
+
+
 def check_native(dev, world, rank):
   from easyparallellibrary_b200.communicators.native import NativeBackend
+  stage("native: create")
   be = NativeBackend(list(range(world)), dev)
+  stage("native: verbs")
   t = torch.full((1024,), float(rank + 1), device=dev)
   be.all_reduce(t)
   assert t[0].item() == world * (world + 1) / 2
@@ -41,6 +47,7 @@ def check_native(dev, world, rank):
   rows = torch.arange(world * 2, device=dev, dtype=torch.float32).view(-1, 1) + 100 * rank
   out, rc = be.all_to_allv(rows, torch.full((world,), 2))
   assert out.shape[0] == 2 * world and out[0, 0].item() == 2 * rank
+  stage("native: p2p")
   if rank == 0:
     be.send(torch.full((4,), 7.0, device=dev), 1); be.wait()
   elif rank == 1:
@@ -64,6 +71,7 @@ def check_native(dev, world, rank):
 def check_symm(dev, world, rank):
   from easyparallellibrary_b200.runtime.symmetric import SignalPad, SymmetricBuffer, _sym_lib
   from easyparallellibrary_b200.ops import _lib
+  stage("symm: alloc")
   n = 256 << 20
   buf = SymmetricBuffer(n, list(range(world)), dev)
   mine = buf.tensor(torch.float32, n // 4)
@@ -71,18 +79,17 @@ def check_symm(dev, world, rank):
   pad = SignalPad(4, list(range(world)), dev)
   pad.barrier(0)
   peer = (rank + 1) % world
-  pt = buf.peer_tensor(peer, torch.float32, n // 4)
-  assert pt[12345].item() == float(peer)
+  src_ptr = buf.peer_ptrs[peer]
   dst = torch.empty(n // 4, device=dev)
   lib = _sym_lib()
   for blocks in (32, 148, 296):
     for _ in range(2):
-      lib.epl_peer_copy(pt.data_ptr(), dst.data_ptr(), n, blocks, _lib.stream())
+      lib.epl_peer_copy(src_ptr, dst.data_ptr(), n, blocks, _lib.stream())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-      lib.epl_peer_copy(pt.data_ptr(), dst.data_ptr(), n, blocks, _lib.stream())
+      lib.epl_peer_copy(src_ptr, dst.data_ptr(), n, blocks, _lib.stream())
     e1.record(); torch.cuda.synchronize()
     log("peer copy (kernel ld over NVLink), %3d CTAs: %.1f GB/s" % (blocks, n * 5 / e0.elapsed_time(e1) / 1e6))
   assert dst[777].item() == float(peer)

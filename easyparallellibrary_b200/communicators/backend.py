@@ -228,6 +228,25 @@ class TorchBackend(object):
     self.group = None
 
 
+def _no_grad_verbs(cls):
+  """Collectives move raw data; autograd rules live in communicators/functional.py."""
+  for name in ("all_reduce", "reduce", "broadcast", "all_gather", "all_gatherv", "reduce_scatter", "all_to_all", "all_to_allv",
+               "all_reduce_async", "reduce_scatter_into", "all_gather_into", "send", "recv"):
+    fn = getattr(cls, name)
+
+    def wrapped(self, *a, __fn=fn, **kw):
+      with torch.no_grad():
+        a = tuple(x.detach() if isinstance(x, torch.Tensor) else x for x in a)
+        return __fn(self, *a, **kw)
+    wrapped.__name__ = name
+    wrapped.__doc__ = fn.__doc__
+    setattr(cls, name, wrapped)
+  return cls
+
+
+_no_grad_verbs(TorchBackend)
+
+
 def make_backend(ranks: Sequence[int], prefer_native: bool = False, device: Optional[torch.device] = None, copy: int = 0):
   ranks = list(ranks)
   if len(ranks) <= 1:

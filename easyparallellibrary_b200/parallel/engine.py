@@ -175,27 +175,60 @@ class Trainer(object):
         if ranks not in dp_groups:
           dp_groups.append(ranks)
     register_groups(dp_groups, copies=cfg.communication.num_communicators)
+    # parameter groups: one per local pipeline stage (data-parallel over that stage's replicas) plus one per
+    # split taskgraph (tensor-parallel shards: reduced only over the replicas that hold the *same* shard)
+    split_owner = {}
+    for ti in self.plan.split_taskgraphs:
+      for p in graph.taskgraphs[ti].parameters:
+        split_owner[id(p)] = ti
+    self.group_keys: List[int] = []
+    group_params: Dict[int, List[nn.Parameter]] = {}
+    group_ranks: Dict[int, List[int]] = {}
+    seen = set()
     for s in self.plan.local_stages:
-      tg_index = self.plan.stage_taskgraphs[s]
-      pl = self.plan.placements[tg_index]
-      comm = CollectiveCommunicator("DATA_PARALLEL_GRADS_REDUCE_%d" % s, pl.dp_ranks, device=self.device)
+      pl = self.plan.placements[self.plan.stage_taskgraphs[s]]
+      mine = []
+      for p in self.stage_modules[s].parameters():
+        if id(p) in seen or not p.requires_grad:
+          continue
+        seen.add(id(p))
+        ti = split_owner.get(id(p))
+        if ti is not None and ti in self.plan.placements:
+          key = 1000 + ti
+          if key not in group_params:
+            group_params[key], group_ranks[key] = [], self.plan.placements[ti].dp_ranks
+          group_params[key].append(p)
+        else:
+          mine.append(p)
+      group_params[s], group_ranks[s] = mine, pl.dp_ranks
+    self.group_keys = [k for k in list(self.plan.local_stages) + sorted(k for k in group_params if k >= 1000)]
+    self.has_split = any(k >= 1000 for k in self.group_keys)
+    extra = []
+    for ti in self.plan.split_taskgraphs:       # every rank registers every shard-replica group (collective creation)
+      n = graph.taskgraphs[ti].strategy.device_count or self.plan.world
+      for k in range(n):
+        ranks = [r for r in range(self.plan.world) if r % n == k]
+        if ranks not in dp_groups and ranks not in extra:
+          extra.append(ranks)
+    register_groups(extra, copies=cfg.communication.num_communicators)
+    self._sharded: Dict[int, bool] = {}
+    for s in self.group_keys:
+      comm = CollectiveCommunicator("DATA_PARALLEL_GRADS_REDUCE_%d" % s, group_ranks[s], device=self.device)
       self.dp_comms[s] = comm
       self._cur_stage = s
-      seen, params = set(), []
-      for p in self.stage_modules[s].parameters():
-        if id(p) not in seen and p.requires_grad and not getattr(p, "epl_tp_sharded_grad_skip", False):
-          seen.add(id(p))
-          params.append(p)
+      params = group_params[s]
       self.sharded = (zero in ("v0", "v1", "v2", "v3") or (cfg.communication.fused_kernels and self.device.type == "cuda"
                                                            and not self.baseline)) and comm.size > 1
+      self._sharded[s] = self.sharded
       shard_world = comm.size if self.sharded else 1
       flat = FlatParameters(params, cfg.communication.max_splits, shard_world, allocator=self._bucket_allocator(comm))
       self.flats[s] = flat
       if comm.size > 1:
         for dt, buf in flat.flat_params.items():
           comm.broadcast(buf, root=0)
-        for b in self.stage_modules[s].buffers():
-          comm.broadcast(b, root=0)
+        if s < 1000:
+          for b in self.stage_modules[s].buffers():
+            comm.broadcast(b, root=0)
       opts = []
       offload = cfg.offload.level == "v0"
       for b in flat.buckets:
@@ -405,7 +438,7 @@ class Trainer(object):
     slot = len(self._pending) % comm.pool.size
     be = comm.pool.backends[slot]
     zero = self.config.zero.level
-    if self.sharded and zero != "v0":
+    if self._sharded[s] and zero != "v0":
       lo, hi = b.shard_range(comm.rank, comm.size)
       w = be.reduce_scatter_into(b.flat_grad[lo:hi], b.flat_grad, "sum", async_op=True)
     else:
@@ -425,12 +458,12 @@ class Trainer(object):
       gnorm = self._grad_norm(reduced=False) * inv
       c = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
       if c < 1.0:                       # each replica clips its own gradient, then the clipped ones are reduced
-        for s_ in self.plan.local_stages:
+        for s_ in self.group_keys:
           for g_ in self.flats[s_].flat_grads.values():
             g_.mul_(c)
     # (2) reduce, last bucket first (its gradients were produced first)
     launched = {(s, b.index) for s, b, _ in self._pending}
-    for s in self.plan.local_stages:
+    for s in self.group_keys:
       for b in reversed(self.flats[s].buckets):
         if (s, b.index) not in launched:
           self._launch_bucket_reduce(s, b)
@@ -441,7 +474,7 @@ class Trainer(object):
     found_inf = False
     if isinstance(self.scaler, (amp_lib.DynamicLossScale, amp_lib.FixedLossScale)):
       bad = torch.zeros(1, device=self.device)
-      for s in self.plan.local_stages:
+      for s in self.group_keys:
         for b in self.flats[s].buckets:
           bad += (~torch.isfinite(b.flat_grad)).any().float()
       for comm in self.dp_comms.values():
@@ -457,27 +490,43 @@ class Trainer(object):
       gnorm = self._grad_norm(reduced=True) * inv / (n if mean else 1)
       coef = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
     # (5) apply
-    for s in self.plan.local_stages:
-      comm, flat, opts = self.dp_comms[s], self.flats[s], self.optimizers[s]
-      scale = inv * coef / (comm.size if mean else 1)
-      groups = max(1, cfg.optimizer.num_apply_group)
-      gathers = []
-      for b, opt in zip(flat.buckets, opts):
-        lo, hi = b.shard_range(comm.rank if self.sharded else 0, comm.size if self.sharded else 1)
-        gshard, pshard = b.flat_grad[lo:hi], b.flat_param[lo:hi]
-        if self.baseline:
-          self._baseline_apply(opt, gshard, pshard, scale)
-        else:
-          n = hi - lo
-          per = (n + groups - 1) // groups
-          for g in range(groups - 1, -1, -1):           # groups applied last to first (optimizer_helper.py:95-120)
-            opt.step(gshard, pshard, scale, g * per, min((g + 1) * per, n), count_step=(g == groups - 1))
-        if self.sharded and comm.size > 1:
-          gathers.append(comm.pool.backends[len(gathers) % comm.pool.size].all_gather_into(b.flat_param, pshard, async_op=True))
-      for w in gathers:
-        if w is not None:
-          w.wait()
+    for s in self.group_keys:
+      self._apply_group(s, mean, inv * coef)
     return False, gnorm
+
+  def _apply_group(self, s: int, mean: bool, scale0: float) -> None:
+    cfg = self.config
+    comm, flat, opts = self.dp_comms[s], self.flats[s], self.optimizers[s]
+    sharded = self._sharded[s]
+    scale = scale0 / (comm.size if (mean and not self.has_split) else 1)
+    groups = max(1, cfg.optimizer.num_apply_group)
+    gathers = []
+    for b, opt in zip(flat.buckets, opts):
+      lo, hi = b.shard_range(comm.rank if sharded else 0, comm.size if sharded else 1)
+      gshard, pshard = b.flat_grad[lo:hi], b.flat_param[lo:hi]
+      if self.baseline:
+        self._baseline_apply(opt, gshard, pshard, scale)
+      else:
+        n = hi - lo
+        per = ((n + groups - 1) // groups + 7) // 8 * 8
+        for g in range(groups - 1, -1, -1):           # groups applied last to first (optimizer_helper.py:95-120)
+          opt.step(gshard, pshard, scale, min(g * per, n), min((g + 1) * per, n), count_step=(g == groups - 1))
+      if sharded and comm.size > 1:
+        gathers.append(comm.pool.backends[len(gathers) % comm.pool.size].all_gather_into(b.flat_param, pshard, async_op=True))
+    for w in gathers:
+      if w is not None:
+        w.wait()
+
+  def _apply_group_library(self, s: int, mean: bool) -> None:
+    """Reduce + apply one parameter group through the library path (used by the fused engine for groups that
+    do not live in symmetric memory, e.g. fp32 or single-replica groups)."""
+    for b in reversed(self.flats[s].buckets):
+      self._launch_bucket_reduce(s, b)
+    for _, _, w in self._pending:
+      if w is not None:
+        w.wait()
+    self._pending = []
+    self._apply_group(s, mean, self.scaler.inv_scale)
 
   def _baseline_apply(self, opt: FlatOptimizer, g, p, scale) -> None:
     from easyparallellibrary_b200.runtime.optimizer import adamw_reference, sgd_reference
@@ -490,16 +539,16 @@ class Trainer(object):
 
   def _grad_norm(self, reduced: bool) -> torch.Tensor:
     sq = torch.zeros(1, device=self.device, dtype=torch.float32)
-    for s in self.plan.local_stages:
+    for s in self.group_keys:
       comm = self.dp_comms[s]
       part = torch.zeros(1, device=self.device, dtype=torch.float32)
       for b in self.flats[s].buckets:
-        if reduced and self.sharded and self.config.zero.level != "v0" and comm.size > 1:
+        if reduced and self._sharded[s] and self.config.zero.level != "v0" and comm.size > 1:
           lo, hi = b.shard_range(comm.rank, comm.size)
           part += b.flat_grad[lo:hi].float().pow(2).sum()
         else:
           part += b.flat_grad.float().pow(2).sum()
-      if reduced and self.sharded and self.config.zero.level != "v0" and comm.size > 1:
+      if reduced and self._sharded[s] and self.config.zero.level != "v0" and comm.size > 1:
         comm.primary.all_reduce(part, "sum")
       sq += part
     if self.plan.pipeline and self.plan.num_stages > 1:
@@ -556,6 +605,7 @@ class Trainer(object):
     sd = {"global_step": self.global_step, "model": {}, "optim": {}, "loss_scale": self.scaler.loss_scale}
     for s in self.plan.local_stages:
       sd["model"][s] = self.stage_modules[s].state_dict()
+    for s in self.group_keys:
       sd["optim"][s] = [o.state_dict() for o in self.optimizers[s]]
     return sd
 
@@ -565,6 +615,7 @@ class Trainer(object):
       self.scaler.loss_scale = sd.get("loss_scale", self.scaler.loss_scale)
     for s in self.plan.local_stages:
       self.stage_modules[s].load_state_dict(sd["model"][s])
+    for s in self.group_keys:
       for o, osd in zip(self.optimizers[s], sd["optim"][s]):
         o.load_state_dict(osd)
 

@@ -42,9 +42,11 @@ class FusedDataParallel(object):
     if not getattr(trainer, "_symm_buffers", None):
       return None
     self = cls(trainer)
-    for s in trainer.plan.local_stages:
+    for s in trainer.group_keys:
       comm = trainer.dp_comms[s]
       flat = trainer.flats[s]
+      if comm.size <= 1 or (s, "grad", torch.bfloat16) not in trainer._symm_buffers and (s, "grad", torch.float16) not in trainer._symm_buffers:
+        continue
       self.pads[s] = SignalPad(len(flat.buckets), comm.ranks, trainer.device, group=getattr(comm.primary, "group", None))
       self.local_sync[s] = torch.zeros(2 * len(flat.buckets), dtype=torch.int32, device=trainer.device)
     return self
@@ -75,7 +77,10 @@ class FusedDataParallel(object):
 
   def reduce_and_apply(self, mean: bool):
     tr = self.trainer
-    for s in tr.plan.local_stages:
+    for s in tr.group_keys:
+      if s not in self.pads:
+        tr._apply_group_library(s, mean)
+        continue
       for bi in range(len(tr.flats[s].buckets) - 1, -1, -1):
-        self.launch_bucket(s, bi, mean)
+        self.launch_bucket(s, bi, mean and not tr.has_split)
     return False, None

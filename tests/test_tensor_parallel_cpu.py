@@ -1,0 +1,140 @@
+"""epl.split tensor-parallel ops on 2 CPU ranks (gloo) against the unsharded computation.
+Mirrors the intent of the reference's split_test.py / resnet_split example (replicate backbone + split head)."""
+import numpy as np
+import torch
+from torch import nn
+
+from dist_utils import run_distributed
+
+
+def _split_head_worker(rank, world, steps=3):
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.ops import tensor_parallel as tp
+  epl.init(epl.Config({"cluster.colocate_split_and_replicate": True}))
+  torch.manual_seed(0)
+  C, H = 11, 8                       # 11 classes over 2 shards -> 6 + 5 (remainder to shard 0)
+  full_w = torch.randn(C, H) * 0.3
+  full_b = torch.randn(C) * 0.1
+  with epl.replicate(device_count=world):
+    backbone = nn.Linear(6, H)
+  with epl.split(device_count=world):
+    head = tp.DistributedDense(H, C)
+    with torch.no_grad():
+      head.weight.copy_(full_w[head.start:head.end])
+      head.bias.copy_(full_b[head.start:head.end])
+
+  class Net(nn.Module):
+    def __init__(self):
+      super().__init__()
+      self.backbone, self.head = backbone, head
+
+    def forward(self, x, y):
+      with epl.split(device_count=world):
+        logits = self.head(torch.tanh(self.backbone(x)))
+        loss = tp.distributed_sparse_softmax_cross_entropy_with_logits(y, logits)
+        pred = tp.distributed_argmax(logits)
+        acc = tp.distributed_equal(pred, y).float().mean()
+      epl.add_to_collection(acc, epl.GraphKeys.LOCAL_MEAN_OBJECTS)
+      return loss
+
+  net = Net()
+  tr = epl.Trainer(net, "sgd", lr=0.1).build()
+  assert tr.has_split and len(tr.group_keys) == 2
+  torch.manual_seed(1)
+  X, Y = torch.randn(steps, 8, 6), torch.randint(0, C, (steps, 8))
+  losses, accs = [], []
+  for i in range(steps):
+    x, y = X[i].chunk(world)[rank], Y[i].chunk(world)[rank]
+    out = tr.step(x, y)
+    losses.append(out.item())
+    accs.append(float(out.collections[epl.GraphKeys.LOCAL_MEAN_OBJECTS][0]))
+  return (losses, accs, backbone.weight.detach().numpy().copy(), head.weight.detach().numpy().copy(), (head.start, head.end),
+          full_w.numpy(), full_b.numpy())
+
+
+def test_replicate_backbone_split_head_matches_unsharded():
+  res = run_distributed(_split_head_worker, 2)
+  full_w, full_b = res[0][5], res[0][6]
+  # unsharded reference in this process
+  torch.manual_seed(0)
+  _ = torch.randn(11, 8), torch.randn(11)
+  backbone = nn.Linear(6, 8)
+  W = nn.Parameter(torch.tensor(full_w))
+  Bb = nn.Parameter(torch.tensor(full_b))
+  opt = torch.optim.SGD(list(backbone.parameters()) + [W, Bb], lr=0.1)
+  torch.manual_seed(1)
+  X, Y = torch.randn(3, 8, 6), torch.randint(0, 11, (3, 8))
+  ref_losses = []
+  for i in range(3):
+    logits = torch.nn.functional.linear(torch.tanh(backbone(X[i])), W, Bb)
+    loss = torch.nn.functional.cross_entropy(logits, Y[i])
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    ref_losses.append(loss.item())
+  for r in res:
+    assert np.allclose(r[0], ref_losses, atol=1e-5), (r[0], ref_losses)
+    assert np.allclose(r[2], backbone.weight.detach().numpy(), atol=1e-5)
+    s, e = r[4]
+    assert np.allclose(r[3], W.detach().numpy()[s:e], atol=1e-5)
+  assert res[0][4] == (0, 6) and res[1][4] == (6, 11)
+  assert res[0][1] == res[1][1]          # accuracy over the gathered batch agrees on both shards
+
+
+def _megatron_worker(rank, world):
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.ops import tensor_parallel as tp
+  epl.init(epl.Config({"cluster.colocate_split_and_replicate": True}))
+  d, T = 8, 12
+  torch.manual_seed(0)
+  W1, b1, W2, b2 = torch.randn(4 * d, d) * 0.2, torch.randn(4 * d) * 0.1, torch.randn(d, 4 * d) * 0.2, torch.randn(d) * 0.1
+  with epl.split(device_count=world):
+    fc1 = tp.ColumnParallelLinear(d, 4 * d, gelu=True)
+    fc2 = tp.RowParallelLinear(4 * d, d)
+    n = 4 * d // world
+    with torch.no_grad():
+      fc1.weight.copy_(W1[rank * n:(rank + 1) * n]); fc1.bias.copy_(b1[rank * n:(rank + 1) * n])
+      fc2.weight.copy_(W2[:, rank * n:(rank + 1) * n]); fc2.bias.copy_(b2)
+  torch.manual_seed(1)
+  x = torch.randn(T, d)
+  xs = x.chunk(world)[rank].clone().requires_grad_()
+  y = fc2(fc1(xs))
+  y.pow(2).sum().backward()
+  return (y.detach().numpy(), xs.grad.numpy(), fc1.weight.grad.numpy(), fc2.weight.grad.numpy(), fc2.bias.grad.numpy())
+
+
+def test_column_row_parallel_pair_matches_unsharded():
+  res = run_distributed(_megatron_worker, 2)
+  d, T = 8, 12
+  torch.manual_seed(0)
+  W1, b1, W2, b2 = [t.requires_grad_() for t in (torch.randn(4 * d, d) * 0.2, torch.randn(4 * d) * 0.1,
+                                                   torch.randn(d, 4 * d) * 0.2, torch.randn(d) * 0.1)]
+  torch.manual_seed(1)
+  x = torch.randn(T, d, requires_grad=True)
+  F = torch.nn.functional
+  y = F.linear(F.gelu(F.linear(x, W1, b1), approximate="tanh"), W2, b2)
+  y.pow(2).sum().backward()
+  n = 4 * d // 2
+  for r, out in enumerate(res):
+    rows = slice(r * T // 2, (r + 1) * T // 2)
+    assert np.allclose(out[0], y.detach().numpy()[rows], atol=1e-5)
+    assert np.allclose(out[1], x.grad.numpy()[rows], atol=1e-5)
+    assert np.allclose(out[2], W1.grad.numpy()[r * n:(r + 1) * n], atol=1e-5)
+    assert np.allclose(out[3], W2.grad.numpy()[:, r * n:(r + 1) * n], atol=1e-5)
+  # the replicated bias sees only the local token shard: summing over the split group gives the true gradient
+  assert np.allclose(res[0][4] + res[1][4], b2.grad.numpy(), atol=1e-5)
+
+
+def test_shard_helpers_and_init():
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.ops import tensor_parallel as tp
+  assert tp.shard_sizes(10, 4) == [4, 2, 2, 2]
+  assert tp.shard_sizes(10, 4, remainder_to_first=False) == [3, 3, 2, 2]
+  assert tp.shard_range(11, 2, 1) == (6, 11)
+  epl.init(init_process_group=False)
+  t = torch.empty(1000, 50)
+  tp.distributed_glorot_uniform_(t, 400, 2000)
+  assert t.abs().max().item() <= (6.0 / 2400) ** 0.5 + 1e-6
+  with epl.split(1):
+    w = tp.add_weight((7, 3))
+    assert w.shape == (7, 3) and w.epl_tp_shard == (0, 0, 7, 7)

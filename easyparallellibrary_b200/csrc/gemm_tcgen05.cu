@@ -49,6 +49,22 @@ struct GemmParams {
   float alpha;
 };
 
+// Fused collective (tensor-parallel) state.  mode 1: all-gather -> GEMM, mode 2: GEMM -> reduce-scatter.
+constexpr int kMaxPeers = 8;
+enum CommMode : int { COMM_NONE = 0, COMM_AG = 1, COMM_RS = 2 };
+struct CommParams {
+  int rank, world;
+  uint32_t epoch;              // strictly increasing per launch on this workspace
+  int copy_ctas;               // mode 1: trailing CTAs of the grid that run the NVLink copy role
+  int rows_per_rank;           // M / world (token rows owned by each rank)
+  uint32_t* flags[kMaxPeers];  // symmetric signal pad of every rank: [0,8) start slots, [8,16) end slots
+  uint32_t* local_sync;        // device-local words: [0] start-go, [1] arrival counter, [2] end-go, [8+r] chunk-r arrivals
+  const void* ag_src[kMaxPeers];   // mode 1: every rank's shard [rows_per_rank, K] (contiguous rows)
+  void* ag_dst;                    // mode 1: local gathered A [M, K] (the buffer map_a describes)
+  void* rs_stage[kMaxPeers];       // mode 2: every rank's staging [world, rows_per_rank, ldd]; this rank writes slot `rank`
+  void* rs_out;                    // mode 2: local reduced output [rows_per_rank, ldd]
+};
+
 EPL_DEVICE float gelu_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
@@ -80,10 +96,10 @@ EPL_DEVICE void tile_coords(int tile, int m_blocks, int n_blocks, int& mb, int& 
 }
 
 template <typename OutT>
-EPL_DEVICE void store_chunk(const GemmParams& p, int row, int col0, const float (&v)[32]) {
-  OutT* drow = reinterpret_cast<OutT*>(p.D) + (size_t)row * p.ldd;
+EPL_DEVICE void store_chunk(const GemmParams& p, void* row_ptr, int col0, const float (&v)[32]) {
+  OutT* drow = reinterpret_cast<OutT*>(row_ptr);
   constexpr int E = 16 / sizeof(OutT);
-  const bool vec_ok = (p.ldd % E == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+  const bool vec_ok = (p.ldd % E == 0) && ((reinterpret_cast<uintptr_t>(row_ptr) & 15) == 0);
 #pragma unroll
   for (int g = 0; g < 32 / E; ++g) {
     const int c = col0 + g * E;
@@ -111,11 +127,83 @@ EPL_DEVICE void store_chunk(const GemmParams& p, int row, int col0, const float 
   }
 }
 
-template <int BN>
+EPL_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+EPL_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+EPL_DEVICE void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+EPL_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// threads [0, world) of the calling CTA: tell every peer "slot[rank] = epoch", wait until every peer told us
+EPL_DEVICE void cross_gpu_signal_wait(const CommParams& c, int slot_base) {
+  if ((int)threadIdx.x < c.world) {
+    __threadfence_system();
+    st_release_sys(c.flags[threadIdx.x] + slot_base + c.rank, c.epoch);
+    while (ld_acquire_sys(c.flags[c.rank] + slot_base + threadIdx.x) < c.epoch) {}
+  }
+}
+
+// m-block visiting order: all-gather starts with the local rows (already here), reduce-scatter ends with them
+template <int kComm>
+EPL_DEVICE int rotate_mb(int mb, int m_blocks, const CommParams& c) {
+  if constexpr (kComm == COMM_NONE) return mb;
+  const int per = max(m_blocks / c.world, 1);
+  const int shift = (kComm == COMM_AG ? c.rank : c.rank + 1) * per;
+  return (mb + shift) % m_blocks;
+}
+
+// ---- copy role of the all-gather -> GEMM kernel: pull every rank's shard into the local gathered buffer ----------
+EPL_DEVICE void ag_copy_role(const GemmParams& p, const CommParams& c, int gemm_ctas) {
+  const int cid = blockIdx.x - gemm_ctas;
+  if (cid == 0) {
+    cross_gpu_signal_wait(c, 0);                       // every rank's shard is ready to be read
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); st_release_gpu(c.local_sync, c.epoch); }
+  } else if (threadIdx.x == 0) {
+    while (ld_acquire_gpu(c.local_sync) < c.epoch) {}
+  }
+  __syncthreads();
+  const size_t chunk_bytes = (size_t)c.rows_per_rank * p.K * 2;
+  const size_t vecs = chunk_bytes / 16;
+  const size_t per_cta = (vecs + c.copy_ctas - 1) / c.copy_ctas;
+  const size_t v0 = (size_t)cid * per_cta, v1 = min(vecs, v0 + per_cta);
+  for (int step = 0; step < c.world; ++step) {
+    const int src = (c.rank + step) % c.world;         // local chunk first, then ring order (spreads load over links)
+    const int4* from = reinterpret_cast<const int4*>(c.ag_src[src]);
+    int4* to = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(c.ag_dst) + (size_t)src * chunk_bytes);
+    size_t i = v0 + threadIdx.x;
+    for (; i + 3 * kGemmThreads < v1; i += 4 * kGemmThreads) {          // 4 x 16 B in flight per thread
+      int4 a = ld_stream(from + i), b = ld_stream(from + i + kGemmThreads);
+      int4 d = ld_stream(from + i + 2 * kGemmThreads), e = ld_stream(from + i + 3 * kGemmThreads);
+      to[i] = a; to[i + kGemmThreads] = b; to[i + 2 * kGemmThreads] = d; to[i + 3 * kGemmThreads] = e;
+    }
+    for (; i < v1; i += kGemmThreads) to[i] = ld_stream(from + i);
+    fence_proxy_async_all();                           // generic-proxy stores -> visible to the TMA (async proxy) reads
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); red_release_gpu_add(c.local_sync + 8 + src, 1u); }
+  }
+  // end barrier: nobody may overwrite its shard before every peer has finished reading it
+  __shared__ int last_copy;
+  if (threadIdx.x == 0) last_copy = (atomicAdd(c.local_sync + 1, 1u) == (uint32_t)c.copy_ctas * c.epoch - 1u);
+  __syncthreads();
+  if (last_copy) cross_gpu_signal_wait(c, 8);
+}
+
+template <int BN, int kComm>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const GemmParams p) {
+                    const GemmParams p, const CommParams c) {
   using L = SmemLayout<BN>;
+  const int gemm_ctas = (kComm == COMM_AG) ? (int)gridDim.x - c.copy_ctas : (int)gridDim.x;
+  if constexpr (kComm == COMM_AG) {
+    if ((int)blockIdx.x >= gemm_ctas) { ag_copy_role(p, c, gemm_ctas); return; }
+  }
   constexpr int kStages = L::kStages;
   constexpr int kTmemCols = 512;                       // 2 accumulator stages of BN (<= 256) fp32 columns
   extern __shared__ unsigned char smem_dyn[];
@@ -145,14 +233,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if constexpr (kComm == COMM_RS) {
+    // every rank's staging buffer is free again (its previous reduction has completed): open the gate for stores
+    if (blockIdx.x == 0 && warp == 0) {
+      cross_gpu_signal_wait(c, 0);
+      __syncwarp();
+      if (lane == 0) { __threadfence(); st_release_gpu(c.local_sync, c.epoch); }
+    }
+  }
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gemm_ctas) {
         int mb, nb;
         tile_coords(tile, m_blocks, n_blocks, mb, nb);
+        mb = rotate_mb<kComm>(mb, m_blocks, c);
         const int m0 = mb * BLOCK_M, n0 = nb * BN;
+        if constexpr (kComm == COMM_AG) {              // the gathered rows of this tile must have landed
+          const int s_lo = m0 / c.rows_per_rank, s_hi = min(m0 + BLOCK_M - 1, p.M - 1) / c.rows_per_rank;
+          for (int sr = s_lo; sr <= s_hi; ++sr)
+            while (ld_acquire_gpu(c.local_sync + 8 + sr) < (uint32_t)c.copy_ctas * c.epoch) {}
+          fence_proxy_async_all();
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * L::kStageBytes;
@@ -187,7 +290,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2, b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gemm_ctas) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -213,11 +316,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ================================ epilogue (warps 2..5) =======================
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    bool rs_go = false;
+    (void)rs_go;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gemm_ctas) {
       int mb, nb;
       tile_coords(tile, m_blocks, n_blocks, mb, nb);
+      mb = rotate_mb<kComm>(mb, m_blocks, c);
       const int row = mb * BLOCK_M + quarter * 32 + lane;
       const int n0 = nb * BN;
+      unsigned char* drow = reinterpret_cast<unsigned char*>(p.D);
+      const size_t out_es = p.out_dtype == EPL_F32 ? 4 : 2;
+      if constexpr (kComm == COMM_RS) {                // the tile goes to the rank that owns these rows
+        if (!rs_go) {
+          if (lane == 0) while (ld_acquire_gpu(c.local_sync) < c.epoch) {}
+          __syncwarp();
+          rs_go = true;
+        }
+        const int owner = min(row / c.rows_per_rank, c.world - 1);
+        drow = reinterpret_cast<unsigned char*>(c.rs_stage[owner]) +
+               ((size_t)c.rank * c.rows_per_rank + (row - owner * c.rows_per_rank)) * p.ldd * out_es;
+      } else {
+        drow += (size_t)row * p.ldd * out_es;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -273,15 +393,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 v[j + e] = (p.epilogue == EPI_DGELU) ? v[j + e] * gelu_grad_f(a8[e]) : v[j + e] + a8[e];
             }
           }
-          if (p.out_dtype == EPL_BF16) store_chunk<__nv_bfloat16>(p, row, col0, v);
-          else if (p.out_dtype == EPL_F32) store_chunk<float>(p, row, col0, v);
-          else store_chunk<__half>(p, row, col0, v);
+          if (p.out_dtype == EPL_BF16) store_chunk<__nv_bfloat16>(p, drow, col0, v);
+          else if (p.out_dtype == EPL_F32) store_chunk<float>(p, drow, col0, v);
+          else store_chunk<__half>(p, drow, col0, v);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (kComm == COMM_RS) {
+      // ---- all of this CTA's tiles are stored; the last CTA of the grid runs the cross-GPU barrier ------------------
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2) {
+        int is_last = 0;
+        if (lane == 0) {
+          __threadfence_system();
+          is_last = (atomicAdd(c.local_sync + 1, 1u) == (uint32_t)gemm_ctas * c.epoch - 1u);
+        }
+        is_last = __shfl_sync(0xffffffffu, is_last, 0);
+        if (is_last) {
+          if (lane < c.world) {
+            __threadfence_system();
+            st_release_sys(c.flags[lane] + 8 + c.rank, c.epoch);          // "my partial tiles are in your staging buffer"
+            while (ld_acquire_sys(c.flags[c.rank] + 8 + lane) < c.epoch) {}
+          }
+          __syncwarp();
+          if (lane == 0) { __threadfence(); st_release_gpu(c.local_sync + 2, c.epoch); }
+        }
+        if (lane == 0) while (ld_acquire_gpu(c.local_sync + 2) < c.epoch) {}
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- local reduction over the `world` staging slots -> rs_out (bf16), 8 columns per thread ----------------------
+      const int et = (warp - 2) * 32 + lane;                              // 0..127
+      const int vec_per_row = p.N / 8;
+      const __nv_bfloat16* stage = reinterpret_cast<const __nv_bfloat16*>(c.rs_stage[c.rank]);
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(c.rs_out);
+      const long total = (long)c.rows_per_rank * vec_per_row;
+      for (long i = (long)blockIdx.x * 128 + et; i < total; i += (long)gemm_ctas * 128) {
+        const int r = (int)(i / vec_per_row), cv = (int)(i % vec_per_row);
+        float accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < c.world; ++w) {
+          Vec<__nv_bfloat16, 8> part = ld_vec<__nv_bfloat16, 8>(stage + ((size_t)w * c.rows_per_rank + r) * p.ldd + cv * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) accv[e] += __bfloat162float(part.v[e]);
+        }
+        Vec<__nv_bfloat16, 8> o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = __float2bfloat16_rn(accv[e]);
+        st_vec<__nv_bfloat16, 8>(out + (size_t)r * p.ldd + cv * 8, o);
+      }
     }
   }
   tc_fence_before();
@@ -325,18 +487,21 @@ static int make_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_sms, cudaStream_t st) {
+template <int BN, int kComm>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, const CommParams& c, int num_sms,
+                       cudaStream_t st) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kComm>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (p.N + BN - 1) / BN;
-  const int grid = std::min(m_blocks * n_blocks, num_sms);
-  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, L::kTotalBytes, st>>>(ma, mb, p);
+  int grid;
+  if (kComm == COMM_NONE) grid = std::min(m_blocks * n_blocks, num_sms);
+  else grid = num_sms;       // fused kernels: the whole grid must be co-resident (CTAs spin on flags), counters assume a fixed size
+  gemm_tcgen05_kernel<BN, kComm><<<grid, kGemmThreads, L::kTotalBytes, st>>>(ma, mb, p, c);
   return EPL_CHECK_LAUNCH();
 }
 
@@ -373,7 +538,51 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
   p.accumulate = accumulate; p.out_dtype = out_dtype; p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.alpha = alpha; p.ab_format = is_fp16 ? 0 : 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (num_sms <= 0) num_sms = kNumSMs;
-  if (bn == 256) return launch_gemm<256>(ma, mb, p, num_sms, st);
-  if (bn == 160) return launch_gemm<160>(ma, mb, p, num_sms, st);
-  return launch_gemm<128>(ma, mb, p, num_sms, st);
+  CommParams c{};
+  if (bn == 256) return launch_gemm<256, COMM_NONE>(ma, mb, p, c, num_sms, st);
+  if (bn == 160) return launch_gemm<160, COMM_NONE>(ma, mb, p, c, num_sms, st);
+  return launch_gemm<128, COMM_NONE>(ma, mb, p, c, num_sms, st);
+}
+
+// Fused tensor-parallel GEMMs.  mode 1 (all-gather -> GEMM): A is the local gathered buffer `ag_dst` [M, K] which the
+// kernel's copy CTAs fill from `ag_src[r]` (each [M/world, K], contiguous).  mode 2 (GEMM -> reduce-scatter): the tiles are
+// written to `rs_stage[owner]` slot `rank`, then reduced into `rs_out` [M/world, ldd] (bf16 only).
+extern "C" int epl_gemm_fused(int mode, const void* A, const void* B, int M, int N, int K, int lda, int ldb, int ldd,
+                              int b_mn_major, const void* bias, void* pre, int epilogue, void* D,
+                              int rank, int world, unsigned epoch, int copy_ctas, void* const* flag_ptrs, void* local_sync,
+                              void* const* ag_src, void* const* rs_stage, void* rs_out, int is_fp16, void* stream) {
+  if (world > kMaxPeers || M % world) return -20;
+  const int bn = pick_bn(N, b_mn_major, 0);
+  CUtensorMap ma, mb;
+  int rc = make_map_2d(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, is_fp16);
+  if (rc) return rc;
+  if (!b_mn_major) rc = make_map_2d(&mb, B, N, K, ldb, BLOCK_K, bn, is_fp16);
+  else rc = make_map_2d(&mb, B, K, N, ldb, 64, BLOCK_K, is_fp16);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.D = D; p.bias = bias; p.pre = pre; p.aux = nullptr; p.epilogue = epilogue;
+  p.accumulate = 0; p.out_dtype = is_fp16 ? EPL_F16 : EPL_BF16; p.a_mn_major = 0; p.b_mn_major = b_mn_major; p.alpha = 1.f;
+  p.ab_format = is_fp16 ? 0 : 1;
+  CommParams c{};
+  c.rank = rank; c.world = world; c.epoch = epoch; c.copy_ctas = copy_ctas; c.rows_per_rank = M / world;
+  c.local_sync = (uint32_t*)local_sync; c.ag_dst = const_cast<void*>(A); c.rs_out = rs_out;
+  for (int i = 0; i < world; ++i) {
+    c.flags[i] = (uint32_t*)flag_ptrs[i];
+    c.ag_src[i] = ag_src ? ag_src[i] : nullptr;
+    c.rs_stage[i] = rs_stage ? rs_stage[i] : nullptr;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == COMM_AG) {
+    if (lda != K || (K % 8)) return -21;
+    if (bn == 256) return launch_gemm<256, COMM_AG>(ma, mb, p, c, kNumSMs, st);
+    if (bn == 160) return launch_gemm<160, COMM_AG>(ma, mb, p, c, kNumSMs, st);
+    return launch_gemm<128, COMM_AG>(ma, mb, p, c, kNumSMs, st);
+  }
+  if (mode == COMM_RS) {
+    if (is_fp16 || (N % 8) || (ldd % 8)) return -21;
+    if (bn == 256) return launch_gemm<256, COMM_RS>(ma, mb, p, c, kNumSMs, st);
+    if (bn == 160) return launch_gemm<160, COMM_RS>(ma, mb, p, c, kNumSMs, st);
+    return launch_gemm<128, COMM_RS>(ma, mb, p, c, kNumSMs, st);
+  }
+  return -22;
 }

@@ -27,7 +27,7 @@ USE_FUSED = True         # flipped off for the baseline measurements
 
 
 def _fused_ok(x: torch.Tensor, group) -> bool:
-  if not (USE_FUSED and x.is_cuda and group.size > 1 and x.dtype in (torch.bfloat16, torch.float16)):
+  if not (USE_FUSED and x.is_cuda and group.size > 1 and x.dtype == torch.bfloat16):
     return False
   try:
     from easyparallellibrary_b200.ops import tp_kernels

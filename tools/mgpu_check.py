@@ -129,6 +129,60 @@ def check_fused(dev, world, rank):
   assert same == 0.0 and diff < 2e-2 and abs(loss_f[-1] - loss_b[-1]) < 0.05
 
 
+def check_tp(dev, world, rank):
+  """Fused all-gather->GEMM and GEMM->reduce-scatter kernels vs the NCCL + separate GEMM path."""
+  from easyparallellibrary_b200.ops import tensor_parallel as tp
+  from easyparallellibrary_b200.ops import tp_fused
+  epl.init(epl.Config({"cluster.colocate_split_and_replicate": True}))
+  with epl.split(world):
+    group = tp.current_tp_group()
+  torch.manual_seed(7)
+  results = {}
+  for (T, K, N) in ((1024 * world, 1024, 4096 // world * world), (8192, 1600, 6400 // world // 8 * 8)):
+    T = T // (128 * world) * (128 * world)
+    xs = (torch.randn(T // world, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    b = torch.randn(N, device=dev).bfloat16()
+    a = (torch.randn(T, K, device=dev) * 0.5).bfloat16()
+    outs = {}
+    for fused in (False, True):
+      tp_fused.USE_FUSED = fused
+      y, pre, xf = tp_fused.ag_gemm(xs, w, group, bias=b, gelu=True)
+      z = tp_fused.gemm_rs(a, w, group)
+      torch.cuda.synchronize()
+      outs[fused] = (y.float(), z.float(), xf.float())
+    dy = (outs[True][0] - outs[False][0]).abs().max().item()
+    dz = (outs[True][1] - outs[False][1]).abs().max().item()
+    dx = (outs[True][2] - outs[False][2]).abs().max().item()
+    ref = outs[False][1].abs().max().item()
+    log("tp T=%d K=%d N=%d: |ag_gemm diff|=%.3e |x_full diff|=%.1e |gemm_rs diff|=%.3e (ref max %.2f)" % (T, K, N, dy, dx, dz, ref))
+    assert dx == 0.0 and dy < 0.1 and dz < 0.02 * ref + 0.1
+    for fused in (False, True):
+      tp_fused.USE_FUSED = fused
+      for name, fn in (("ag_gemm", lambda: tp_fused.ag_gemm(xs, w, group, bias=b, gelu=True)), ("gemm_rs", lambda: tp_fused.gemm_rs(a, w, group))):
+        for _ in range(3):
+          fn()
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+          fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        results[(T, K, N, name, fused)] = t.item()
+    for name in ("ag_gemm", "gemm_rs"):
+      fl = 2.0 * T * K * N
+      nv = (world - 1) / world * T * (K if name == "ag_gemm" else N) * 2
+      log("  %-8s NCCL+GEMM %.3f ms | fused %.3f ms | speedup %.2fx | roofline max(gemm %.3f ms @1.4PF, nvlink %.3f ms @770GB/s)" % (
+          name, results[(T, K, N, name, False)], results[(T, K, N, name, True)],
+          results[(T, K, N, name, False)] / results[(T, K, N, name, True)], fl / 1.4e12, nv / 770e6))
+  tp_fused.USE_FUSED = True
+  if rank == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({"%d_%d_%d_%s_%s" % k: v for k, v in results.items()}, open("gpurun_out/tp_fused_bench_w%d.json" % world, "w"))
+
+
 def main():
   dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
   rank, world = dist.get_rank(), dist.get_world_size()
@@ -141,6 +195,8 @@ def main():
     check_symm(dev, world, rank)
   if "fused" in what:
     check_fused(dev, world, rank)
+  if "tp" in what:
+    check_tp(dev, world, rank)
   dist.barrier()
   log("MGPU CHECK PASSED")
   dist.destroy_process_group()

@@ -264,3 +264,75 @@ int epl_fused_rs_adam_ag(void* const* grad_ptrs, void* const* param_ptrs, void* 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// K5 — all-to-all over NVLink peer memory (MoE dispatch / combine).
+//   send: local [world, seg] buffer; segment j is stored straight into rank j's symmetric receive buffer at
+//   slot `rank` (P2P 16-byte stores), bracketed by release/acquire flag barriers in peer memory.  One kernel,
+//   no NCCL; the reference issues 2*world ncclSend/ncclRecv per call (tensorflow_nccl.h:186-206).
+// ---------------------------------------------------------------------------------------------------------
+namespace epl {
+struct A2AArgs {
+  PeerTable recv;           // every rank's receive buffer [world, seg_bytes]
+  PeerTable flags;          // signal pads: [0,8) start, [8,16) end
+  const int4* send;         // local [world, seg_bytes]
+  uint32_t* local_sync;     // [0] go, [1] arrivals
+  int64_t seg_vecs;         // 16-byte vectors per segment
+  int rank, world;
+  uint32_t epoch;
+};
+
+__global__ void __launch_bounds__(512) alltoall_p2p_kernel(const A2AArgs a) {
+  // start: every peer has finished consuming its receive buffer from the previous call
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + a.rank, a.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + threadIdx.x) < a.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.local_sync), "r"(a.epoch) : "memory"); }
+  } else if (threadIdx.x == 0) {
+    uint32_t v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.local_sync) : "memory"); } while (v < a.epoch);
+  }
+  __syncthreads();
+  const int64_t total = a.seg_vecs * a.world;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int p = (int)(i / a.seg_vecs);
+    const int dst = (a.rank + p) % a.world;                     // rotate so all links carry traffic at once
+    const int64_t off = i - (int64_t)p * a.seg_vecs;
+    int4 v = a.send[(int64_t)dst * a.seg_vecs + off];
+    st_peer(reinterpret_cast<int4*>(a.recv.ptr[dst]) + (int64_t)a.rank * a.seg_vecs + off, v);
+  }
+  // end: my segments have landed everywhere and everyone's segments have landed here
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x * a.epoch - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + kMaxPeers + a.rank, a.epoch);
+    while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + kMaxPeers + threadIdx.x) < a.epoch) {}
+  }
+}
+}  // namespace epl
+
+extern "C" int epl_alltoall_p2p(const void* send, void* const* recv_ptrs, void* const* flag_ptrs, void* local_sync,
+                                int64_t seg_bytes, int rank, int world, unsigned epoch, int blocks, void* stream) {
+  if (world > epl::kMaxPeers || (seg_bytes & 15)) return -20;
+  epl::A2AArgs a;
+  for (int i = 0; i < epl::kMaxPeers; ++i) {
+    a.recv.ptr[i] = i < world ? recv_ptrs[i] : nullptr;
+    a.flags.ptr[i] = i < world ? flag_ptrs[i] : nullptr;
+  }
+  a.send = (const int4*)send; a.local_sync = (uint32_t*)local_sync; a.seg_vecs = seg_bytes / 16;
+  a.rank = rank; a.world = world; a.epoch = epoch;
+  if (blocks <= 0) blocks = 64;
+  epl::alltoall_p2p_kernel<<<std::min(blocks, epl::kNumSMs), 512, 0, (cudaStream_t)stream>>>(a);
+  return EPL_CHECK_LAUNCH();
+}

@@ -1,0 +1,178 @@
+"""Checkpoint utilities.
+
+Reference (``epl/runtime/saver.py``, ``hooks.py:531-590``): only the first constructor rank writes (every
+worker writes its own shard when a ``split`` taskgraph exists); restore on the first constructor then
+broadcast; ``ShardingLoader`` (46-128) warm-starts from another checkpoint with a name map and per-tensor
+slices; ``MemoryEfficientBuilder`` (145-207) saves in bounded-memory buckets (>= 50 MB, sequential, via CPU).
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+from typing import Any, Callable, Dict, Iterable, List, Optional, Tuple
+
+import torch
+
+BUCKET_BYTES = 50 << 20
+
+
+def _rank() -> int:
+  import torch.distributed as dist
+  return dist.get_rank() if dist.is_initialized() else 0
+
+
+class MemoryEfficientBuilder(object):
+  """Sharded save: tensors are staged on the host bucket by bucket (each >= ``bucket_bytes``) and written one
+  file per bucket, so peak extra host memory is one bucket, never the whole model."""
+
+  def __init__(self, directory: str, bucket_bytes: int = BUCKET_BYTES):
+    self.dir, self.bucket_bytes = directory, bucket_bytes
+
+  def save(self, state: Dict[str, torch.Tensor], prefix: str = "model", extra: Optional[Dict[str, Any]] = None) -> List[str]:
+    os.makedirs(self.dir, exist_ok=True)
+    index, files, cur, cur_bytes = {}, [], {}, 0
+
+    def flush():
+      nonlocal cur, cur_bytes
+      if not cur:
+        return
+      name = "%s-%05d.pt" % (prefix, len(files))
+      torch.save(cur, os.path.join(self.dir, name))
+      files.append(name)
+      cur, cur_bytes = {}, 0
+
+    for k, v in state.items():
+      t = v.detach().to("cpu") if isinstance(v, torch.Tensor) else v
+      cur[k] = t
+      index[k] = len(files)
+      cur_bytes += t.numel() * t.element_size() if isinstance(t, torch.Tensor) else 0
+      if cur_bytes >= self.bucket_bytes:
+        flush()
+    flush()
+    with open(os.path.join(self.dir, prefix + ".index.json"), "w") as f:
+      json.dump({"files": files, "index": {k: files[i] for k, i in index.items()}, "extra": extra or {}}, f)
+    return files
+
+  def load(self, prefix: str = "model") -> Tuple[Dict[str, torch.Tensor], Dict[str, Any]]:
+    meta = json.load(open(os.path.join(self.dir, prefix + ".index.json")))
+    out = {}
+    for name in meta["files"]:
+      out.update(torch.load(os.path.join(self.dir, name), map_location="cpu"))
+    return out, meta.get("extra", {})
+
+
+class ShardingLoader(object):
+  """Initialise a model from a checkpoint of a *differently shaped* run.
+
+  ``assign_map``: ``{checkpoint_name_regex: model_name_template}`` (``\\1`` style groups) or a callable;
+  ``sharding_info``: ``{model_name: (begin, size)}`` per dimension slices — e.g. load this rank's slice of an
+  unsharded tensor into a tensor-parallel shard.  Parameters tagged ``epl_tp_shard`` get their slice automatically.
+  """
+
+  def __init__(self, checkpoint: Dict[str, torch.Tensor], assign_map=None, sharding_info: Optional[Dict[str, Tuple]] = None):
+    self.ckpt, self.assign_map, self.sharding_info = checkpoint, assign_map, sharding_info or {}
+
+  def _target_name(self, ckpt_name: str) -> Optional[str]:
+    if self.assign_map is None:
+      return ckpt_name
+    if callable(self.assign_map):
+      return self.assign_map(ckpt_name)
+    for pat, tmpl in self.assign_map.items():
+      if re.fullmatch(pat, ckpt_name):
+        return re.sub(pat, tmpl, ckpt_name)
+    return None
+
+  def load_into(self, module: torch.nn.Module, strict: bool = False) -> List[str]:
+    params = dict(module.named_parameters())
+    params.update(dict(module.named_buffers()))
+    loaded = []
+    for ck, tensor in self.ckpt.items():
+      name = self._target_name(ck)
+      if name is None or name not in params:
+        continue
+      dst = params[name]
+      src = tensor
+      info = self.sharding_info.get(name)
+      if info is None and hasattr(dst, "epl_tp_shard") and tuple(src.shape) != tuple(dst.shape):
+        dim, lo, hi, _total = dst.epl_tp_shard
+        info = tuple((lo, hi - lo) if d == dim else (0, src.shape[d]) for d in range(src.dim()))
+      if info is not None:
+        if isinstance(info[0], int):
+          info = (info,)
+        for d, (begin, size) in enumerate(info):
+          src = src.narrow(d, begin, size)
+      if tuple(src.shape) != tuple(dst.shape):
+        if strict:
+          raise ValueError("shape mismatch for %s: checkpoint %s vs model %s" % (name, tuple(src.shape), tuple(dst.shape)))
+        continue
+      with torch.no_grad():
+        dst.copy_(src.to(dst.dtype))
+      loaded.append(name)
+    if strict:
+      missing = set(params) - set(loaded)
+      if missing:
+        raise KeyError("checkpoint misses %s" % sorted(missing))
+    return loaded
+
+
+def save_checkpoint(trainer, directory: str, bucket_bytes: int = BUCKET_BYTES) -> Optional[List[str]]:
+  """First replica of every pipeline stage writes its stage; with split taskgraphs every rank writes its shards."""
+  trainer.build()
+  must_write = trainer.is_first_replica or getattr(trainer, "has_split", False)
+  files = None
+  if must_write:
+    sub = os.path.join(directory, "rank%d" % _rank()) if (trainer.plan.num_stages > 1 or trainer.has_split) else directory
+    builder = MemoryEfficientBuilder(sub, bucket_bytes)
+    state = {}
+    for s in trainer.plan.local_stages:
+      for k, v in trainer.stage_modules[s].state_dict().items():
+        state["stage%d.%s" % (s, k)] = v
+    opt = {}
+    for s in trainer.group_keys:
+      for i, o in enumerate(trainer.optimizers[s]):
+        for k, v in o.state_dict().items():
+          if isinstance(v, torch.Tensor):
+            opt["g%d.b%d.%s" % (s, i, k)] = v
+          else:
+            opt["g%d.b%d.%s" % (s, i, k)] = torch.tensor(v) if isinstance(v, (int, float)) else v
+    files = builder.save(state, "model", {"global_step": trainer.global_step, "loss_scale": trainer.scaler.loss_scale})
+    if trainer.is_first_replica or trainer.has_split or any(trainer._sharded.values()):
+      builder.save(opt, "optim")
+  import torch.distributed as dist
+  if dist.is_initialized():
+    dist.barrier()
+  return files
+
+
+def load_checkpoint(trainer, directory: str) -> int:
+  """Restore on every rank from the files written by ``save_checkpoint``; returns the restored global step."""
+  trainer.build()
+  sub = os.path.join(directory, "rank%d" % _rank())
+  if not os.path.isdir(sub):
+    # written by the first replica only: find the writer that holds the same stage
+    sub = directory
+    if trainer.plan.num_stages > 1:
+      stage = trainer.plan.local_stages[0]
+      sub = os.path.join(directory, "rank%d" % trainer.plan.stage_ranks[stage][0][0])
+  builder = MemoryEfficientBuilder(sub)
+  state, extra = builder.load("model")
+  for s in trainer.plan.local_stages:
+    prefix = "stage%d." % s
+    sd = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
+    own = trainer.stage_modules[s].state_dict()
+    for k, v in sd.items():
+      if k in own:
+        own[k].copy_(v.to(own[k].dtype))
+  if os.path.exists(os.path.join(sub, "optim.index.json")):
+    opt, _ = builder.load("optim")
+    for s in trainer.group_keys:
+      for i, o in enumerate(trainer.optimizers[s]):
+        pre = "g%d.b%d." % (s, i)
+        if pre + "master" in opt and opt[pre + "master"].numel() == o.master.numel():
+          o.load_state_dict({"step": int(opt[pre + "step"]), "master": opt[pre + "master"],
+                             "m": opt.get(pre + "m"), "v": opt.get(pre + "v")})
+  trainer.global_step = int(extra.get("global_step", 0))
+  if hasattr(trainer.scaler, "loss_scale") and "loss_scale" in extra:
+    trainer.scaler.loss_scale = extra["loss_scale"]
+  return trainer.global_step

@@ -155,8 +155,16 @@ class Trainer(object):
       _materialize(m, self.device)
     if cfg.gradient_checkpoint.type:
       from easyparallellibrary_b200.runtime.gradient_checkpoint import apply_gradient_checkpoint
+      nodes = None
+      if cfg.gradient_checkpoint.type == constant.GC_AUTO and self.example_inputs is not None and self.plan.num_stages == 1:
+        from easyparallellibrary_b200.ir.capture import trace_module_costs
+        try:
+          ex = [_to_device(x, self.device) for x in self.example_inputs]
+          nodes = trace_module_costs(self.model, ex)
+        except Exception as e:  # pragma: no cover - tracing is best effort
+          get_logger().warning("auto gradient checkpoint: tracing failed (%s); using module structure", e)
       for m in local:
-        wrapped = apply_gradient_checkpoint(m, cfg.gradient_checkpoint.type, None,
+        wrapped = apply_gradient_checkpoint(m, cfg.gradient_checkpoint.type, nodes,
                                             graph.get_collection(GraphKeys.GC_CHECKPOINTS),
                                             cfg.gradient_checkpoint.end_taskgraph)
         get_logger().info("gradient checkpoint: %d segment(s)", len(wrapped))
@@ -387,6 +395,8 @@ class Trainer(object):
       flat.zero_grad()
     self._pending = []
     batch = tuple(_to_device(x, self.device) for x in batch)
+    if self.compute_dtype is not None and batch and isinstance(batch[0], torch.Tensor) and batch[0].is_floating_point():
+      batch = (batch[0].to(self.compute_dtype),) + batch[1:]          # the model input follows the compute dtype (AMP)
     micro = _split_batch(batch, M)
     losses: List[torch.Tensor] = []
     collected: List["OrderedDict[str, List[Any]]"] = []

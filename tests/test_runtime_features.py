@@ -1,0 +1,206 @@
+"""Single-process CPU tests of the runtime features: gradient checkpoint, offload, AMP loss scale, grouped apply,
+checkpoint save/resume, ShardingLoader, IO slicing, profiler hooks, auto stage search, launcher command lines.
+Tolerances follow the reference's A/B tests (|dloss| < 1e-6 offload / grouped apply, < 1e-5 checkpoint)."""
+import json
+import os
+
+import pytest
+import torch
+from torch import nn
+
+import easyparallellibrary_b200 as epl
+
+
+def _net(seed=0):
+  torch.manual_seed(seed)
+  blocks = [nn.Sequential(nn.Linear(16, 16), nn.Tanh(), nn.Linear(16, 16), nn.Dropout(0.0)) for _ in range(6)]
+  return nn.Sequential(nn.Linear(8, 16), *blocks, nn.Linear(16, 1))
+
+
+def _run(conf, steps=4, opt="adamw", **kw):
+  epl.init(epl.Config(conf), init_process_group=False)
+  with epl.replicate(1):
+    model = _net()
+  tr = epl.Trainer(model, opt, loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2, **kw)
+  torch.manual_seed(1)
+  X, Y = torch.randn(steps, 8, 8), torch.randn(steps, 8, 1)
+  return [tr.step(X[i], Y[i]).item() for i in range(steps)], tr
+
+
+def test_gradient_checkpoint_auto_and_collection_match_plain():
+  base, _ = _run({})
+  auto, tr = _run({"gradient_checkpoint.type": "auto"}, example_inputs=[torch.randn(8, 8)])
+  assert max(abs(a - b) for a, b in zip(base, auto)) < 1e-5
+  from easyparallellibrary_b200.runtime.gradient_checkpoint import _Checkpointed
+  assert sum(isinstance(m, _Checkpointed) for m in tr.model.modules()) == 6      # the six repeated blocks
+  epl.init(epl.Config({"gradient_checkpoint.type": "collection"}), init_process_group=False)
+  with epl.replicate(1):
+    model = _net()
+  for blk in list(model)[1:4]:
+    epl.add_to_collection(blk, epl.GraphKeys.GC_CHECKPOINTS)
+  tr = epl.Trainer(model, "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2)
+  torch.manual_seed(1)
+  X, Y = torch.randn(4, 8, 8), torch.randn(4, 8, 1)
+  coll = [tr.step(X[i], Y[i]).item() for i in range(4)]
+  assert max(abs(a - b) for a, b in zip(base, coll)) < 1e-5
+  with pytest.raises(RuntimeError):
+    _run({"gradient_checkpoint.type": "collection"})
+
+
+def test_offload_and_grouped_apply_match_plain():
+  base, _ = _run({})
+  off, tr = _run({"offload.level": "v0"})
+  assert max(abs(a - b) for a, b in zip(base, off)) < 1e-6
+  from easyparallellibrary_b200.runtime.offload import OffloadedOptimizer
+  assert all(isinstance(o, OffloadedOptimizer) for o in tr.optimizers[0])
+  grp, _ = _run({"optimizer.num_apply_group": 4})
+  assert max(abs(a - b) for a, b in zip(base, grp)) < 1e-6
+  ga, _ = _run({"pipeline.num_micro_batch": 4})
+  assert max(abs(a - b) for a, b in zip(base, ga)) < 1e-5
+
+
+def test_dynamic_loss_scale_skips_and_recovers():
+  from easyparallellibrary_b200.runtime.amp import DynamicLossScale, FixedLossScale, make_scaler
+  s = DynamicLossScale(initial=2.0 ** 15, increment_period=3)
+  assert s.update(True) and s.loss_scale == 2.0 ** 14
+  assert not s.update(False) and not s.update(False)
+  assert not s.update(False) and s.loss_scale == 2.0 ** 15            # doubled after 3 good steps
+  for _ in range(40):
+    s.update(True)
+  assert s.loss_scale == 1.0                                           # floor
+  assert isinstance(make_scaler("o1", 128.0), FixedLossScale) and make_scaler("o1", 128.0).loss_scale == 128.0
+  assert make_scaler("", "dynamic").loss_scale == 1.0
+  # an overflowing step is skipped (weights untouched) and the scale halves — reference dnn_data_parallel.py:68-74
+  epl.init(epl.Config({"amp.level": "O1", "amp.loss_scale": "dynamic"}), init_process_group=False)
+  with epl.replicate(1):
+    model = nn.Linear(4, 1)
+  tr = epl.Trainer(model, "sgd", loss_fn=lambda o, y: ((o.float() - y) ** 2).mean(), lr=0.1)
+  x, y = torch.full((2, 4), 3e4), torch.zeros(2, 1)
+  before = None
+  out = tr.step(x, y)
+  w0 = model.weight.detach().float().clone()
+  assert out.skipped and tr.scaler.loss_scale == 2.0 ** 14 and tr.global_step == 0
+  out = tr.step(x * 0, y)
+  assert not out.skipped and tr.global_step == 1
+
+
+def test_checkpoint_save_and_resume(tmp_path):
+  from easyparallellibrary_b200.runtime.saver import load_checkpoint, save_checkpoint
+  losses, tr = _run({}, steps=3)
+  save_checkpoint(tr, str(tmp_path), bucket_bytes=1024)
+  assert len([f for f in os.listdir(tmp_path) if f.startswith("model-")]) > 1       # bounded-memory buckets
+  torch.manual_seed(5)
+  x, y = torch.randn(8, 8), torch.randn(8, 1)
+  expect = [tr.step(x, y).item() for _ in range(2)]
+  _, tr2 = _run({}, steps=0)
+  step = load_checkpoint(tr2.build(), str(tmp_path))
+  assert step == 3 and tr2.global_step == 3
+  got = [tr2.step(x, y).item() for _ in range(2)]
+  assert max(abs(a - b) for a, b in zip(expect, got)) < 1e-6 and tr2.global_step == 5
+
+
+def test_sharding_loader_rename_and_slice():
+  from easyparallellibrary_b200.ops import tensor_parallel as tp
+  from easyparallellibrary_b200.runtime.saver import ShardingLoader
+  ckpt = {"enc.w": torch.arange(24.0).view(6, 4), "enc.b": torch.arange(6.0)}
+  m = nn.Linear(4, 3)
+  loaded = ShardingLoader(ckpt, {r"enc\.w": "weight", r"enc\.b": "bias"}, {"weight": ((3, 3), (0, 4)), "bias": (3, 3)}).load_into(m)
+  assert sorted(loaded) == ["bias", "weight"]
+  assert torch.equal(m.weight.data, ckpt["enc.w"][3:6]) and torch.equal(m.bias.data, ckpt["enc.b"][3:6])
+  epl.init(init_process_group=False)
+  with epl.split(1):
+    holder = nn.Module()
+    holder.w = tp.add_weight((6, 4))
+  assert ShardingLoader({"w": ckpt["enc.w"]}).load_into(holder) == ["w"]
+
+
+def test_io_slicing_cases():
+  from easyparallellibrary_b200.utils.io_slicing import slice_files
+  f = list(range(12))
+  assert slice_files(f, [1, 1], 0) == f[:6] and slice_files(f, [1, 1], 1) == f[6:]
+  assert slice_files(f, [2, 1], 0) == f[:8] and slice_files(f, [2, 1], 1) == f[8:]
+  assert slice_files(f, [2, 2], 1) == f[6:]                              # gcd-normalised
+  assert slice_files(list(range(10)), [1, 1, 1], 0, drop_last_files=True) == [0, 1, 2]
+  assert slice_files(list(range(10)), [1, 1, 1], 2, drop_last_files=True) == [6, 7, 8]
+  assert slice_files(list(range(10)), [1, 1, 1], 0, unbalanced_io_slicing=True) == [0, 1, 2, 3]
+  assert sorted(slice_files([0, 1], [1, 1, 1], 1)) == [0, 1]              # too few files: everyone reads all, rotated
+  with pytest.raises(RuntimeError):
+    slice_files([0, 1], [1, 1, 1], 1, drop_last_files=True)
+
+
+def test_profiler_hooks(tmp_path):
+  from easyparallellibrary_b200.profiler import FlopsProfilerHook, MemoryProfilerHook, profile_flops, profile_memory
+  epl.init(init_process_group=False)
+  with epl.replicate(1):
+    model = _net()
+  fl = profile_flops(model, [torch.randn(8, 8)], by="op")
+  assert fl["Linear"] == 2.0 * 8 * (8 * 16 + 12 * 16 * 16 + 16) and fl["__total__"] >= fl["Linear"]
+  tr = epl.Trainer(model, "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2)
+  fh, mh = FlopsProfilerHook(3 * fl["__total__"], use_cuda_events=False), MemoryProfilerHook(output_dir=str(tmp_path))
+  tr.hooks += [fh, mh]
+  for _ in range(3):
+    tr.step(torch.randn(8, 8), torch.randn(8, 1))
+  s = fh.summary()
+  assert s["tflops"] > 0 and 0 < s["median_step_s"]
+  assert mh.save() and os.path.exists(os.path.join(tmp_path, "memory_timeline.csv"))
+  mem = profile_memory(tr)
+  assert mem["weights"] == mem["gradients"] > 0 and mem["optimizer_state_device"] >= 2 * mem["weights"]
+
+
+def test_auto_parallel_stage_search():
+  epl.init(epl.Config({"auto.auto_parallel": True, "pipeline.num_stages": 3, "pipeline.num_micro_batch": 2}), init_process_group=False)
+  model = _net()
+  tr = epl.Trainer(model, "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2, example_inputs=[torch.randn(4, 8)]).build()
+  g = epl.Graph.get()
+  assert len(g.taskgraphs) == 3 and tr.plan.num_stages == 3
+  sizes = [len(list(tr.stage_modules[s])) for s in range(3)]
+  assert sum(sizes) == 8 and max(sizes) - min(sizes) <= 2
+  out = tr.step(torch.randn(4, 8), torch.randn(4, 1))          # colocated on one device: stages run back to back
+  assert out.loss is not None
+
+
+def test_launcher_command_lines():
+  from easyparallellibrary_b200.utils import launcher
+  args = launcher.parse(["--num_workers", "2", "--gpu_per_worker", "2", "train.py", "--lr", "1"])
+  cmds = launcher.build_commands(args)
+  assert [c["rank"] for c in cmds] == [0, 1, 2, 3]
+  assert cmds[3]["env"]["WORLD_SIZE"] == "4" and cmds[3]["env"]["LOCAL_RANK"] == "3" and cmds[3]["argv"][-2:] == ["--lr", "1"]
+  tf = json.loads(cmds[2]["env"]["TF_CONFIG"])
+  assert tf["task"] == {"type": "worker", "index": 1} and len(tf["cluster"]["worker"]) == 2
+  args = launcher.parse(["--num_workers", "4", "--gpu_per_worker", "8", "--machine_list", "10.0.0.1:29500,10.0.0.2:29500",
+                         "--machine_rank", "1", "run.sh"])
+  cmds = launcher.build_commands(args)
+  assert len(cmds) == 16 and cmds[0]["rank"] == 16 and cmds[0]["env"]["MASTER_ADDR"] == "10.0.0.1" and cmds[0]["argv"][0] == "bash"
+
+
+def test_models_build_and_step_on_cpu():
+  from easyparallellibrary_b200.models.bert import Bert, BertConfig
+  from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config
+  from easyparallellibrary_b200.models.moe_transformer import MoEConfig, MoETransformer
+  from easyparallellibrary_b200.models.resnet import ResNet50
+  epl.init(init_process_group=False)
+  with epl.replicate(1):
+    m = GPT2(GPT2Config.named("tiny"))
+  tr = epl.Trainer(m, "adamw", lr=1e-3)
+  x = torch.randint(0, 512, (2, 32))
+  a, b = tr.step(x, x).item(), tr.step(x, x).item()
+  assert b < a
+  epl.init(init_process_group=False)
+  m = GPT2(GPT2Config.named("tiny", num_pipeline_stages=2, tie_embeddings=False))
+  assert len(epl.Graph.get().taskgraphs) == 2 and epl.Graph.get().taskgraph_of(m.h[1]).index == 1
+  epl.init(epl.Config({"cluster.colocate_split_and_replicate": True}), init_process_group=False)
+  epl.set_default_strategy(epl.replicate(1))
+  moe = MoETransformer(MoEConfig(vocab_size=128, d_model=32, d_ff=64, n_layer=2, n_head=4, num_experts=4, n_positions=32))
+  tr = epl.Trainer(moe, "adamw", lr=1e-3)
+  x = torch.randint(0, 128, (2, 16))
+  assert tr.step(x, x).loss.isfinite()
+  epl.init(init_process_group=False)
+  with epl.replicate(1):
+    bert = Bert(BertConfig.named("tiny"))
+  tr = epl.Trainer(bert, "adamw", lr=1e-3)
+  ids, pos = torch.randint(0, 1024, (2, 16)), torch.randint(0, 16, (2,))
+  assert tr.step(ids, pos, pos).loss.isfinite()
+  epl.init(epl.Config({"cluster.colocate_split_and_replicate": True}), init_process_group=False)
+  r = ResNet50(num_classes=64, width=8, layers=(1, 1, 1, 1), split_head=True)
+  tr = epl.Trainer(r, "sgd", lr=1e-2)
+  assert tr.step(torch.randn(2, 3, 32, 32), torch.randint(0, 64, (2,))).loss.isfinite() and tr.has_split

@@ -220,6 +220,7 @@ class Trainer(object):
           extra.append(ranks)
     register_groups(extra, copies=cfg.communication.num_communicators)
     self._sharded: Dict[int, bool] = {}
+    self.zero3: Dict[int, Any] = {}
     for s in self.group_keys:
       comm = CollectiveCommunicator("DATA_PARALLEL_GRADS_REDUCE_%d" % s, group_ranks[s], device=self.device)
       self.dp_comms[s] = comm
@@ -229,6 +230,15 @@ class Trainer(object):
                                                            and not self.baseline)) and comm.size > 1
       self._sharded[s] = self.sharded
       shard_world = comm.size if self.sharded else 1
+      if zero == "v3" and s < 1000:
+        from easyparallellibrary_b200.parallel.zero3 import Zero3Engine
+        root = self.stage_modules[s]
+        units = sequential_layers(root) or [c for c in root.children()]
+        covered = {id(p) for u in units for p in u.parameters()}
+        if any(id(p) not in covered for p in root.parameters()):
+          units = [root]                         # parameters live directly on the root: treat it as one unit
+        self.zero3[s] = Zero3Engine(self, s, units, comm)
+        params = []
       flat = FlatParameters(params, cfg.communication.max_splits, shard_world, allocator=self._bucket_allocator(comm))
       self.flats[s] = flat
       if comm.size > 1:
@@ -393,6 +403,8 @@ class Trainer(object):
     graph.pop_collections()
     for flat in self.flats.values():
       flat.zero_grad()
+    for z in self.zero3.values():
+      z.zero_grad()
     self._pending = []
     batch = tuple(_to_device(x, self.device) for x in batch)
     if self.compute_dtype is not None and batch and isinstance(batch[0], torch.Tensor) and batch[0].is_floating_point():
@@ -418,6 +430,8 @@ class Trainer(object):
           scaled = scaled / M
         with phase_scope(ModelPhase.BACKWARD):
           scaled.backward()
+    for z in self.zero3.values():
+      z.finish_backward()
     with phase_scope(ModelPhase.APPLY):
       skipped, gnorm = self._reduce_and_apply(mean)
     self.global_step += 0 if skipped else 1
@@ -487,6 +501,8 @@ class Trainer(object):
       for s in self.group_keys:
         for b in self.flats[s].buckets:
           bad += (~torch.isfinite(b.flat_grad)).any().float()
+        if s in self.zero3:
+          bad += self.zero3[s].has_non_finite()
       for comm in self.dp_comms.values():
         if comm.size > 1:
           comm.primary.all_reduce(bad, "max")
@@ -509,6 +525,8 @@ class Trainer(object):
     comm, flat, opts = self.dp_comms[s], self.flats[s], self.optimizers[s]
     sharded = self._sharded[s]
     scale = scale0 / (comm.size if (mean and not self.has_split) else 1)
+    if s in self.zero3:
+      self.zero3[s].apply(scale)
     groups = max(1, cfg.optimizer.num_apply_group)
     gathers = []
     for b, opt in zip(flat.buckets, opts):
@@ -561,6 +579,8 @@ class Trainer(object):
       if reduced and self._sharded[s] and self.config.zero.level != "v0" and comm.size > 1:
         comm.primary.all_reduce(part, "sum")
       sq += part
+      if s in self.zero3:
+        sq += self.zero3[s].grad_sq_norm()
     if self.plan.pipeline and self.plan.num_stages > 1:
       sq = self.pipe.all_reduce_over_stages(sq)
     return sq.sqrt()
@@ -610,6 +630,8 @@ class Trainer(object):
       return self._forward_loss(batch, kwargs)
     finally:
       self.model.train(was)
+      for z in self.zero3.values():
+        z.release_all()
 
   def state_dict(self) -> Dict[str, Any]:
     sd = {"global_step": self.global_step, "model": {}, "optim": {}, "loss_scale": self.scaler.loss_scale}

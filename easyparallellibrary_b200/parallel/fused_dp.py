@@ -23,7 +23,7 @@ class FusedDataParallel(object):
     cfg = trainer.config
     return (trainer.device.type == "cuda" and not trainer.baseline and cfg.communication.fused_kernels
             and 1 < comm.size <= 8 and trainer.max_grad_norm is None and cfg.offload.level == ""
-            and cfg.zero.level in ("", "v0", "v1") and trainer.opt_kind in ("adam", "adamw")
+            and cfg.zero.level in ("", "v0", "v1", "v2") and trainer.opt_kind in ("adam", "adamw")
             and cfg.optimizer.num_apply_group == 1
             and trainer.compute_dtype in (torch.bfloat16, torch.float16) and not isinstance(
                 trainer.scaler, __import__("easyparallellibrary_b200.runtime.amp", fromlist=["DynamicLossScale"]).DynamicLossScale))

@@ -1,0 +1,596 @@
+// Flash attention forward + backward on tcgen05 / TMEM / TMA (sm_100a), head dimension 64.
+//
+// Layouts are chosen so that attention plugs between the QKV GEMM and the output projection with no
+// transposes or copies:   qkv  : [B, S, 3, H, 64] bf16  (exactly the output of the fused QKV linear)
+//                         out  : [B, S, H, 64]    bf16  (exactly the input of the projection linear)
+//                         dqkv : [B, S, 3, H, 64] bf16  (exactly the upstream gradient of the QKV linear)
+//
+// Forward: one CTA per (128-query tile, head, batch).  Warp 0 = TMA producer (Q once, then a 2-stage K/V ring),
+// warp 1 = single-thread tcgen05.mma issuer, warps 2-5 = softmax (one query row per thread).  Per 128-key tile:
+//   S = Q K^T (TMEM, 128 cols) -> online softmax in registers (two tcgen05.ld passes: max, then exp2) -> P (bf16) into
+//   swizzled shared memory -> O_t = P V (TMEM, 64 cols) -> O = O * alpha + O_t in registers.
+// 113 KB of shared memory and 256 TMEM columns per CTA, so two CTAs share an SM and one CTA's softmax overlaps the
+// other's MMAs.
+//
+// Backward: one CTA per (128-key tile, head, batch) looping over the query tiles that see it.  Five GEMMs per tile pair
+// (S = Q K^T, dP = dO V^T, dV += P^T dO, dK += dS^T Q, dQ_t = dS K), all on tcgen05 with K-major or MN-major shared-
+// memory descriptors over the *same* TMA-loaded tiles; dV/dK accumulate in TMEM across the loop, dQ tiles are reduced
+// into an fp32 buffer with atomics and converted once at the end.
+//
+// The reference computes attention as unfused softmax(QK^T)V framework ops (examples/bert/modeling.py attention_layer).
+#include "epl_common.cuh"
+#include <algorithm>
+#include <cstdio>
+
+namespace epl {
+
+constexpr int kD = 64;                  // head dimension
+constexpr int kTile = 128;              // queries / keys per tile
+constexpr int kAttnThreads = 192;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kNegBig = -1.0e30f;
+
+EPL_DEVICE void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// 16 consecutive fp32 columns of this thread's TMEM lane
+EPL_DEVICE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+
+// write 8 bf16 (one 16-byte chunk) of row `r`, logical chunk `c` (0..15) of a [128 x 128] bf16 tile stored as two
+// 128B-swizzled atoms of [128 rows x 128 B]
+EPL_DEVICE void st_swizzled_chunk(unsigned char* base, int r, int c, const uint32_t (&w)[4]) {
+  unsigned char* p = base + (c >> 3) * (kTile * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct AttnParams {
+  int B, S, H;
+  float scale;            // 1/sqrt(D)
+  int causal;
+  __nv_bfloat16* out;     // fwd: [B,S,H,64]
+  float* lse;             // [B,H,S]  (natural-log units)
+  // backward only
+  const float* delta;     // [B,H,S]  rowsum(dO * O)
+  float* dq_acc;          // [B,S,H,64] fp32, zero on entry
+  __nv_bfloat16* dqkv;    // [B,S,3,H,64]
+};
+
+// ================================================================================================================
+// forward
+// ================================================================================================================
+struct FwdSmem {
+  static constexpr int kQ = 0;
+  static constexpr int kK = kQ + kTile * 128;            // 2 stages
+  static constexpr int kV = kK + 2 * kTile * 128;        // 2 stages
+  static constexpr int kP = kV + 2 * kTile * 128;        // 32 KB
+  static constexpr int kBar = kP + 2 * kTile * 128;
+  static constexpr int kTotal = kBar + 128;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBar);
+  uint64_t* kv_full = bar_q + 1;        // [2]
+  uint64_t* kv_empty = kv_full + 2;     // [2]
+  uint64_t* s_full = kv_empty + 2;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* o_full = p_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tiles = (p.S + kTile - 1) / kTile;
+  const int qt = q_tiles - 1 - (int)blockIdx.x;          // heaviest (causal) tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * kTile;
+  const int n_kv = p.causal ? qt + 1 : q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_qkv);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, kTile * 128);
+      tma_load_3d(smem + FwdSmem::kQ, &map_qkv, bar_q, h * kD, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * kTile * 128);
+        tma_load_3d(smem + FwdSmem::kK + s * kTile * 128, &map_qkv, &kv_full[s], (p.H + h) * kD, j * kTile, b);
+        tma_load_3d(smem + FwdSmem::kV + s * kTile * 128, &map_qkv, &kv_full[s], (2 * p.H + h) * kD, j * kTile, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(kTile, kTile, 1, 0, 0);      // S = Q K^T : both K-major
+      const uint32_t idesc_o = make_idesc_f16(kTile, kD, 1, 0, 1);         // O = P V   : A K-major, B (V) MN-major
+      const uint32_t sq = smem_u32(smem + FwdSmem::kQ), sp = smem_u32(smem + FwdSmem::kP);
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t sk = smem_u32(smem + FwdSmem::kK + s * kTile * 128), sv = smem_u32(smem + FwdSmem::kV + s * kTile * 128);
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        // S(j) = Q K(j)^T.  (S(j-1) has been consumed: p_ready(j-1) was awaited before P V(j-1) was issued.)
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_f16(tmem_s, make_smem_desc_sw128(sq + k * 32, 16, 1024), make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
+        umma_commit(s_full);
+        // O_t(j) = P(j) V(j) once the softmax warps have written P(j) (they have also drained O_t(j-1) by then)
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(sp + (kk >> 2) * (kTile * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, kTile * 128, 1024);
+          umma_f16(tmem_o, da, db, idesc_o, kk != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                     // query row inside the tile
+    const int qidx = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float c = p.scale * kLog2e;
+    float m = kNegBig, l = 0.f;
+    float o[kD];
+#pragma unroll
+    for (int d = 0; d < kD; ++d) o[d] = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int k0 = j * kTile;
+      const bool need_mask = (k0 + kTile > p.S) || (p.causal && j == qt);
+      // pass 1: row maximum
+      float mx = kNegBig;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + lane_addr + ch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float s = __uint_as_float(v[t]);
+          if (need_mask) {
+            const int kidx = k0 + ch * 32 + t;
+            if (kidx >= p.S || (p.causal && kidx > qidx)) s = kNegBig;
+          }
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f((m - m_new) * c);
+      const float mc = m_new * c;
+      // the previous P V product must be folded into O before P is overwritten
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_o + lane_addr + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) o[ch * 32 + t] += __uint_as_float(v[t]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < kD; ++d) o[d] *= alpha;
+      // pass 2: probabilities -> bf16 -> swizzled shared memory
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + lane_addr + ch * 32, v);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float s = __uint_as_float(v[t]);
+          float e = exp2f(s * c - mc);
+          if (need_mask) {
+            const int kidx = k0 + ch * 32 + t;
+            if (kidx >= p.S || (p.causal && kidx > qidx)) e = 0.f;
+          }
+          pr[t] = e;
+          rowsum += e;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2(pr[g * 8 + 2 * e], pr[g * 8 + 2 * e + 1]);
+          st_swizzled_chunk(smem + FwdSmem::kP, r, ch * 4 + g, w);
+        }
+      }
+      l = l * alpha + rowsum;
+      m = m_new;
+      tc_fence_before();
+      fence_proxy_async();                                 // generic-proxy smem writes -> visible to the UMMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    // last P V
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_o + lane_addr + ch * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) o[ch * 32 + t] += __uint_as_float(v[t]);
+    }
+    if (qidx < p.S) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* dst = p.out + (((size_t)b * p.S + qidx) * p.H + h) * kD;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 w;
+        w.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
+        w.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
+        w.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
+        w.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + g * 8) = w;
+      }
+      p.lse[((size_t)b * p.H + h) * p.S + qidx] = m * p.scale + logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+// ================================================================================================================
+// backward
+// ================================================================================================================
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]; one warp per (b,s,h) row
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                                          float* __restrict__ delta, int B, int S, int H) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (int64_t)B * S * H) return;
+  const __nv_bfloat162 a = reinterpret_cast<const __nv_bfloat162*>(o + row * kD)[lane];
+  const __nv_bfloat162 g = reinterpret_cast<const __nv_bfloat162*>(d_o + row * kD)[lane];
+  float2 af = __bfloat1622float2(a), gf = __bfloat1622float2(g);
+  float s = warp_sum(af.x * gf.x + af.y * gf.y);
+  if (lane == 0) {
+    const int64_t bs = row / H;
+    const int hh = (int)(row % H);
+    const int64_t bb = bs / S, ss = bs % S;
+    delta[(bb * H + hh) * S + ss] = s;
+  }
+}
+
+// dq (bf16, inside dqkv) <- dq_acc (fp32) * 1 ; 8 elements per thread
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
+                                                               int64_t rows, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // over rows * H * 8 chunks
+  const int64_t total = rows * H * (kD / 8);
+  if (i >= total) return;
+  const int64_t row = i / (H * (kD / 8));
+  const int rem = (int)(i % (H * (kD / 8)));
+  const int hh = rem / (kD / 8), ch = rem % (kD / 8);
+  const float4 a = reinterpret_cast<const float4*>(acc + (row * H + hh) * kD + ch * 8)[0];
+  const float4 b2 = reinterpret_cast<const float4*>(acc + (row * H + hh) * kD + ch * 8)[1];
+  uint4 w;
+  w.x = pack_bf16x2(a.x, a.y); w.y = pack_bf16x2(a.z, a.w); w.z = pack_bf16x2(b2.x, b2.y); w.w = pack_bf16x2(b2.z, b2.w);
+  *reinterpret_cast<uint4*>(dqkv + (row * 3 * H + hh) * kD + ch * 8) = w;
+}
+
+struct BwdSmem {
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + kTile * 128;
+  static constexpr int kQ = kV + kTile * 128;            // 2 stages
+  static constexpr int kDO = kQ + 2 * kTile * 128;       // 2 stages
+  static constexpr int kP = kDO + 2 * kTile * 128;       // 32 KB
+  static constexpr int kDS = kP + 2 * kTile * 128;       // 32 KB
+  static constexpr int kBar = kDS + 2 * kTile * 128;
+  static constexpr int kTotal = kBar + 128;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const AttnParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBar);
+  uint64_t* q_full = bar_kv + 1;       // [2]
+  uint64_t* q_empty = q_full + 2;      // [2]
+  uint64_t* sdp_full = q_empty + 2;
+  uint64_t* pds_ready = sdp_full + 1;
+  uint64_t* dq_full = pds_ready + 1;
+  uint64_t* acc_full = dq_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (p.S + kTile - 1) / kTile;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kt * kTile;
+  const int i_begin = p.causal ? kt : 0;
+  const int n_q = tiles - i_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_do);
+    mbar_init(bar_kv, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_ready, 4); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dk = tmem + 320, t_dq = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_kv, 2 * kTile * 128);
+      tma_load_3d(smem + BwdSmem::kK, &map_qkv, bar_kv, (p.H + h) * kD, k0, b);
+      tma_load_3d(smem + BwdSmem::kV, &map_qkv, bar_kv, (2 * p.H + h) * kD, k0, b);
+      for (int n = 0; n < n_q; ++n) {
+        const int s = n & 1, i = i_begin + n;
+        mbar_wait(&q_empty[s], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[s], 2 * kTile * 128);
+        tma_load_3d(smem + BwdSmem::kQ + s * kTile * 128, &map_qkv, &q_full[s], h * kD, i * kTile, b);
+        tma_load_3d(smem + BwdSmem::kDO + s * kTile * 128, &map_do, &q_full[s], h * kD, i * kTile, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc_f16(kTile, kTile, 1, 0, 0);     // S, dP: K-major x K-major
+      const uint32_t id_acc = make_idesc_f16(kTile, kD, 1, 1, 1);      // dV, dK: A^T (MN-major) x B (MN-major)
+      const uint32_t id_dq = make_idesc_f16(kTile, kD, 1, 0, 1);       // dQ: dS (K-major) x K (MN-major)
+      const uint32_t sk = smem_u32(smem + BwdSmem::kK), sv = smem_u32(smem + BwdSmem::kV);
+      const uint32_t sp = smem_u32(smem + BwdSmem::kP), sds = smem_u32(smem + BwdSmem::kDS);
+      mbar_wait(bar_kv, 0);
+      for (int n = 0; n < n_q; ++n) {
+        const int s = n & 1;
+        const uint32_t sq = smem_u32(smem + BwdSmem::kQ + s * kTile * 128), sdo = smem_u32(smem + BwdSmem::kDO + s * kTile * 128);
+        mbar_wait(&q_full[s], (n >> 1) & 1);       // (S / dP of the previous tile were consumed before pds_ready(n-1))
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          umma_f16(t_s, make_smem_desc_sw128(sq + k * 32, 16, 1024), make_smem_desc_sw128(sk + k * 32, 16, 1024), id_s, k != 0);
+          umma_f16(t_dp, make_smem_desc_sw128(sdo + k * 32, 16, 1024), make_smem_desc_sw128(sv + k * 32, 16, 1024), id_s, k != 0);
+        }
+        umma_commit(sdp_full);
+        mbar_wait(pds_ready, n & 1);                        // P and dS are in shared memory
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk) {
+          // dV += P^T dO ; dK += dS^T Q   (contraction over the 128 queries: 16 rows per MMA)
+          const uint64_t a_p = make_smem_desc_sw128(sp + kk * 2048, kTile * 128, 1024);
+          const uint64_t a_ds = make_smem_desc_sw128(sds + kk * 2048, kTile * 128, 1024);
+          const uint64_t b_do = make_smem_desc_sw128(sdo + kk * 2048, kTile * 128, 1024);
+          const uint64_t b_q = make_smem_desc_sw128(sq + kk * 2048, kTile * 128, 1024);
+          umma_f16(t_dv, a_p, b_do, id_acc, (n | kk) != 0);
+          umma_f16(t_dk, a_ds, b_q, id_acc, (n | kk) != 0);
+          // dQ_t = dS K   (contraction over the 128 keys)
+          const uint64_t a_dsk = make_smem_desc_sw128(sds + (kk >> 2) * (kTile * 128) + (kk & 3) * 32, 16, 1024);
+          const uint64_t b_k = make_smem_desc_sw128(sk + kk * 2048, kTile * 128, 1024);
+          umma_f16(t_dq, a_dsk, b_k, id_dq, kk != 0);
+        }
+        umma_commit(dq_full);
+        umma_commit(&q_empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float c = p.scale * kLog2e;
+    for (int n = 0; n < n_q; ++n) {
+      const int i = i_begin + n;
+      const int qidx = i * kTile + r;
+      const bool q_ok = qidx < p.S;
+      const float lse2 = q_ok ? p.lse[((size_t)b * p.H + h) * p.S + qidx] * kLog2e : 0.f;
+      const float dlt = q_ok ? p.delta[((size_t)b * p.H + h) * p.S + qidx] : 0.f;
+      const bool need_mask = (k0 + kTile > p.S) || (p.causal && i == kt) || !q_ok;
+      mbar_wait(sdp_full, n & 1);
+      tc_fence_after();
+      if (n > 0) {
+        // dQ tile of the previous iteration -> fp32 accumulation buffer (also frees P / dS for rewriting)
+        mbar_wait(dq_full, (n - 1) & 1);
+        tc_fence_after();
+        const int qprev = (i - 1) * kTile + r;
+        float* dst = p.dq_acc + (((size_t)b * p.S + qprev) * p.H + h) * kD;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_dq + lane_addr + ch * 32, v);
+          tmem_ld_wait();
+          if (qprev < p.S) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) atomicAdd(dst + ch * 32 + t, __uint_as_float(v[t]) * p.scale);
+          }
+        }
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t sv_[32], dpv[32];
+        tmem_ld_32x32(t_s + lane_addr + ch * 32, sv_);
+        tmem_ld_32x32(t_dp + lane_addr + ch * 32, dpv);
+        tmem_ld_wait();
+        float pr[32], ds[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float e = exp2f(__uint_as_float(sv_[t]) * c - lse2);
+          if (need_mask) {
+            const int kidx = k0 + ch * 32 + t;
+            if (!q_ok || kidx >= p.S || (p.causal && kidx > qidx)) e = 0.f;
+          }
+          pr[t] = e;
+          ds[t] = e * (__uint_as_float(dpv[t]) - dlt);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4], w2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            w[e] = pack_bf16x2(pr[g * 8 + 2 * e], pr[g * 8 + 2 * e + 1]);
+            w2[e] = pack_bf16x2(ds[g * 8 + 2 * e], ds[g * 8 + 2 * e + 1]);
+          }
+          st_swizzled_chunk(smem + BwdSmem::kP, r, ch * 4 + g, w);
+          st_swizzled_chunk(smem + BwdSmem::kDS, r, ch * 4 + g, w2);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_ready);
+    }
+    // last dQ tile
+    {
+      mbar_wait(dq_full, (n_q - 1) & 1);
+      tc_fence_after();
+      const int qlast = (i_begin + n_q - 1) * kTile + r;
+      float* dst = p.dq_acc + (((size_t)b * p.S + qlast) * p.H + h) * kD;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_dq + lane_addr + ch * 32, v);
+        tmem_ld_wait();
+        if (qlast < p.S) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) atomicAdd(dst + ch * 32 + t, __uint_as_float(v[t]) * p.scale);
+        }
+      }
+    }
+    // dK, dV of this key tile -> dqkv (row = key index)
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int kidx = k0 + r;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {            // 0: dV (slot 2), 1: dK (slot 1)
+      const uint32_t src = which == 0 ? t_dv : t_dk;
+      const float mul = which == 0 ? 1.f : p.scale;
+      __nv_bfloat16* dst = p.dqkv + ((((size_t)b * p.S + kidx) * 3 + (which == 0 ? 2 : 1)) * p.H + h) * kD;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(src + lane_addr + ch * 32, v);
+        tmem_ld_wait();
+        if (kidx < p.S) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * mul, __uint_as_float(v[g * 8 + 1]) * mul);
+            w.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * mul, __uint_as_float(v[g * 8 + 3]) * mul);
+            w.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * mul, __uint_as_float(v[g * 8 + 5]) * mul);
+            w.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * mul, __uint_as_float(v[g * 8 + 7]) * mul);
+            *reinterpret_cast<uint4*>(dst + ch * 32 + g * 8) = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn attn_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+// [B, S, cols] bf16, box {64, 128, 1}
+static int make_map_3d(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t S, uint64_t cols) {
+  EncodeTiledFn enc = attn_get_encode();
+  if (!enc) return -10;
+  cuuint64_t dims[3] = {cols, S, B};
+  cuuint64_t strides[2] = {cols * 2, S * cols * 2};
+  cuuint32_t box[3] = {kD, kTile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
+}  // namespace epl
+using namespace epl;
+
+extern "C" int epl_attn_fwd(const void* qkv, void* out, void* lse, int B, int S, int H, float scale, int causal, void* stream) {
+  CUtensorMap map;
+  int rc = make_map_3d(&map, qkv, B, S, (uint64_t)3 * H * kD);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  AttnParams p{};
+  p.B = B; p.S = S; p.H = H; p.scale = scale; p.causal = causal; p.out = (__nv_bfloat16*)out; p.lse = (float*)lse;
+  dim3 grid((S + kTile - 1) / kTile, H, B);
+  attn_fwd_kernel<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(map, p);
+  return EPL_CHECK_LAUNCH();
+}
+
+// dq_acc: fp32 [B,S,H,64] scratch (zeroed here); delta: fp32 [B,H,S] scratch
+extern "C" int epl_attn_bwd(const void* qkv, const void* out, const void* d_out, const void* lse, void* delta, void* dq_acc,
+                            void* dqkv, int B, int S, int H, float scale, int causal, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap map_qkv, map_do;
+  int rc = make_map_3d(&map_qkv, qkv, B, S, (uint64_t)3 * H * kD);
+  if (rc) return rc;
+  rc = make_map_3d(&map_do, d_out, B, S, (uint64_t)H * kD);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int64_t rows = (int64_t)B * S * H;
+  attn_delta_kernel<<<(int)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)d_out, (float*)delta, B, S, H);
+  cudaMemsetAsync(dq_acc, 0, (size_t)rows * kD * sizeof(float), st);
+  AttnParams p{};
+  p.B = B; p.S = S; p.H = H; p.scale = scale; p.causal = causal; p.lse = (float*)const_cast<void*>(lse);
+  p.delta = (const float*)delta; p.dq_acc = (float*)dq_acc; p.dqkv = (__nv_bfloat16*)dqkv;
+  dim3 grid((S + kTile - 1) / kTile, H, B);
+  attn_bwd_kernel<<<grid, kAttnThreads, BwdSmem::kTotal, st>>>(map_qkv, map_do, p);
+  const int64_t chunks = (int64_t)B * S * H * (kD / 8);
+  attn_dq_convert_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>((const float*)dq_acc, (__nv_bfloat16*)dqkv, (int64_t)B * S, H);
+  return EPL_CHECK_LAUNCH();
+}

@@ -74,10 +74,9 @@ class BertLayer(nn.Module):
 
   def forward(self, x):
     B, S, d = x.shape
-    qkv = self.qkv(x).view(B, S, 3, self.heads, d // self.heads)
-    q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
-    a = attention(q, k, v, causal=False).transpose(1, 2).reshape(B, S, d)
+    from easyparallellibrary_b200.ops.attention import attention_packed
     from easyparallellibrary_b200.ops.linear import linear
+    a = attention_packed(self.qkv(x).view(B, S, 3, self.heads, d // self.heads), causal=False)
     x = self.ln1(linear(a, self.proj.weight, self.proj.bias, residual=x))
     return self.ln2(mlp(x, self.fc.weight, self.fc.bias, self.out.weight, self.out.bias, residual=x))
 
@@ -105,9 +104,8 @@ class BertLayerTP(nn.Module):
     S = self.seq_len
     qkv = self.qkv(x_shard)                        # [T, 3d/N]  (all-gather -> GEMM)
     T = qkv.shape[0]
-    qkv = qkv.view(T // S, S, 3, self.heads_local, self.head_dim)
-    q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
-    a = attention(q, k, v, causal=False).transpose(1, 2).reshape(T, self.heads_local * self.head_dim)
+    from easyparallellibrary_b200.ops.attention import attention_packed
+    a = attention_packed(qkv.view(T // S, S, 3, self.heads_local, self.head_dim), causal=False).reshape(T, -1)
     x_shard = self.ln1(x_shard + self.proj(a))     # GEMM -> reduce-scatter
     return self.ln2(x_shard + self.out(self.fc(x_shard)))
 

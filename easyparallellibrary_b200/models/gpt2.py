@@ -86,11 +86,11 @@ class SelfAttention(nn.Module):
 
   def forward(self, x, residual=None):
     B, S, d = x.shape
-    qkv = self.qkv(x).view(B, S, 3, self.n_head, d // self.n_head)
-    q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)            # [B, H, S, hd] views
-    y = attention(q, k, v, causal=True)
+    from easyparallellibrary_b200.ops.attention import attention_packed
     from easyparallellibrary_b200.ops.linear import linear
-    return linear(y.transpose(1, 2).reshape(B, S, d), self.proj.weight, self.proj.bias, residual=residual)
+    qkv = self.qkv(x).view(B, S, 3, self.n_head, d // self.n_head)
+    y = attention_packed(qkv, causal=True)                    # [B, S, d] — no permutes / copies on either side
+    return linear(y, self.proj.weight, self.proj.bias, residual=residual)
 
 
 class MLP(nn.Module):

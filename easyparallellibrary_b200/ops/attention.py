@@ -27,6 +27,20 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = 
   return torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal, dropout_p=dropout_p)
 
 
+def attention_packed(qkv: torch.Tensor, causal: bool = True) -> torch.Tensor:
+  """``qkv``: ``[B, S, 3, H, D]`` (output of a fused QKV projection) -> ``[B, S, H*D]``."""
+  if _IMPL != "sdpa" and qkv.is_cuda:
+    from easyparallellibrary_b200.ops import attention_kernel
+    if attention_kernel.supported_packed(qkv):
+      return attention_kernel.flash_attention_packed(qkv, causal)
+    if _IMPL == "epl":
+      raise RuntimeError("hand-written attention kernel does not support this input (needs bf16, head dim 64, contiguous)")
+  B, S, _, H, D = qkv.shape
+  q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
+  y = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal)
+  return y.transpose(1, 2).reshape(B, S, H * D)
+
+
 def attention_reference(q, k, v, causal: bool = True) -> torch.Tensor:
   """Plain fp32 softmax(QK^T)V — the numerics reference for kernel tests."""
   qf, kf, vf = q.float(), k.float(), v.float()

@@ -249,3 +249,27 @@ def test_layernorm_fork_and_residual_linear():
   _close(y, yr, 3e-2, 5e-2, "block y")
   for name, t, r in zip("x g b w wb w1 b1 w2 b2".split(), params, ref):
     _close(t.grad, r.grad, 4e-2, 4e-2 * r.grad.abs().max().item(), "block d" + name)
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("B,S,H", [(2, 256, 3), (1, 1024, 2), (2, 200, 2), (1, 384, 4)])
+def test_flash_attention_packed(B, S, H, causal):
+  """tcgen05 flash attention fwd + bwd vs fp32 softmax(QK^T)V autograd."""
+  from easyparallellibrary_b200.ops.attention_kernel import flash_attention_packed
+  torch.manual_seed(0)
+  D = 64
+  qkv = (torch.randn(B, S, 3, H, D, device=DEV) * 0.8).bfloat16().requires_grad_()
+  dout = torch.randn(B, S, H * D, device=DEV).bfloat16()
+  out = flash_attention_packed(qkv, causal)
+  out.backward(dout)
+  ref_in = qkv.detach().float().requires_grad_()
+  q, k, v = ref_in.permute(2, 0, 3, 1, 4).unbind(0)
+  s = q @ k.transpose(-1, -2) / math.sqrt(D)
+  if causal:
+    s = s.masked_fill(~torch.ones(S, S, dtype=torch.bool, device=DEV).tril(), float("-inf"))
+  ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, H * D)
+  ref.backward(dout.float())
+  _close(out, ref, 2e-2, 2e-2, "attn out")
+  g, gr = qkv.grad.float(), ref_in.grad
+  for idx, name in enumerate(("dq", "dk", "dv")):
+    _close(g[:, :, idx], gr[:, :, idx], 3e-2, 3e-2 * gr[:, :, idx].abs().max().item(), "attn " + name)

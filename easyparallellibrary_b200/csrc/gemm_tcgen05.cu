@@ -51,12 +51,12 @@ struct GemmParams {
 
 // Fused collective (tensor-parallel) state.  mode 1: all-gather -> GEMM, mode 2: GEMM -> reduce-scatter.
 constexpr int kMaxPeers = 8;
-enum CommMode : int { COMM_NONE = 0, COMM_AG = 1, COMM_RS = 2 };
+enum CommMode : int { COMM_NONE = 0, COMM_AG = 1, COMM_RS = 2, COMM_AGB = 3 };   // AGB: the gathered operand is B (ZeRO-3 weights)
 struct CommParams {
   int rank, world;
   uint32_t epoch;              // strictly increasing per launch on this workspace
   int copy_ctas;               // mode 1: trailing CTAs of the grid that run the NVLink copy role
-  int rows_per_rank;           // M / world (token rows owned by each rank)
+  int rows_per_rank;           // rows of the gathered operand owned by each rank (M / world, or N / world for COMM_AGB)
   uint32_t* flags[kMaxPeers];  // symmetric signal pad of every rank: [0,8) start slots, [8,16) end slots
   uint32_t* local_sync;        // device-local words: [0] start-go, [1] arrival counter, [2] end-go, [8+r] chunk-r arrivals
   const void* ag_src[kMaxPeers];   // mode 1: every rank's shard [rows_per_rank, K] (contiguous rows)
@@ -84,6 +84,14 @@ struct SmemLayout {
   static constexpr int kBarrierOffset = kStages * kStageBytes;
   static constexpr int kTotalBytes = kBarrierOffset + 256 + 1024;   // barriers + alignment slack
 };
+
+// weight-gather order: all m-blocks of one n-block before the next n-block, starting with the n-blocks whose weights
+// are local; the A panel (activations) stays L2-resident across n-blocks
+EPL_DEVICE void tile_coords_n_outer(int tile, int m_blocks, int n_blocks, int rank, int world, int& mb, int& nb) {
+  const int per = max(n_blocks / world, 1);
+  nb = (tile / m_blocks + rank * per) % n_blocks;
+  mb = tile % m_blocks;
+}
 
 EPL_DEVICE void tile_coords(int tile, int m_blocks, int n_blocks, int& mb, int& nb) {
   const int per_group = kGroupM * n_blocks;
@@ -152,7 +160,7 @@ EPL_DEVICE void cross_gpu_signal_wait(const CommParams& c, int slot_base) {
 // m-block visiting order: all-gather starts with the local rows (already here), reduce-scatter ends with them
 template <int kComm>
 EPL_DEVICE int rotate_mb(int mb, int m_blocks, const CommParams& c) {
-  if constexpr (kComm == COMM_NONE) return mb;
+  if constexpr (kComm == COMM_NONE || kComm == COMM_AGB) return mb;
   const int per = max(m_blocks / c.world, 1);
   const int shift = (kComm == COMM_AG ? c.rank : c.rank + 1) * per;
   return (mb + shift) % m_blocks;
@@ -200,8 +208,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p, const CommParams c) {
   using L = SmemLayout<BN>;
-  const int gemm_ctas = (kComm == COMM_AG) ? (int)gridDim.x - c.copy_ctas : (int)gridDim.x;
-  if constexpr (kComm == COMM_AG) {
+  const int gemm_ctas = (kComm == COMM_AG || kComm == COMM_AGB) ? (int)gridDim.x - c.copy_ctas : (int)gridDim.x;
+  if constexpr (kComm == COMM_AG || kComm == COMM_AGB) {
     if ((int)blockIdx.x >= gemm_ctas) { ag_copy_role(p, c, gemm_ctas); return; }
   }
   constexpr int kStages = L::kStages;
@@ -247,9 +255,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gemm_ctas) {
         int mb, nb;
-        tile_coords(tile, m_blocks, n_blocks, mb, nb);
+        if constexpr (kComm == COMM_AGB) tile_coords_n_outer(tile, m_blocks, n_blocks, c.rank, c.world, mb, nb);
+        else tile_coords(tile, m_blocks, n_blocks, mb, nb);
         mb = rotate_mb<kComm>(mb, m_blocks, c);
         const int m0 = mb * BLOCK_M, n0 = nb * BN;
+        if constexpr (kComm == COMM_AGB) {             // the gathered weight rows of this tile must have landed
+          const int s_lo = n0 / c.rows_per_rank, s_hi = min(n0 + BN - 1, p.N - 1) / c.rows_per_rank;
+          for (int sr = s_lo; sr <= s_hi; ++sr)
+            while (ld_acquire_gpu(c.local_sync + 8 + sr) < (uint32_t)c.copy_ctas * c.epoch) {}
+          fence_proxy_async_all();
+        }
         if constexpr (kComm == COMM_AG) {              // the gathered rows of this tile must have landed
           const int s_lo = m0 / c.rows_per_rank, s_hi = min(m0 + BLOCK_M - 1, p.M - 1) / c.rows_per_rank;
           for (int sr = s_lo; sr <= s_hi; ++sr)
@@ -320,7 +335,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     (void)rs_go;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gemm_ctas) {
       int mb, nb;
-      tile_coords(tile, m_blocks, n_blocks, mb, nb);
+      if constexpr (kComm == COMM_AGB) tile_coords_n_outer(tile, m_blocks, n_blocks, c.rank, c.world, mb, nb);
+      else tile_coords(tile, m_blocks, n_blocks, mb, nb);
       mb = rotate_mb<kComm>(mb, m_blocks, c);
       const int row = mb * BLOCK_M + quarter * 32 + lane;
       const int n0 = nb * BN;
@@ -551,7 +567,7 @@ extern "C" int epl_gemm_fused(int mode, const void* A, const void* B, int M, int
                               int b_mn_major, const void* bias, void* pre, int epilogue, void* D,
                               int rank, int world, unsigned epoch, int copy_ctas, void* const* flag_ptrs, void* local_sync,
                               void* const* ag_src, void* const* rs_stage, void* rs_out, int is_fp16, void* stream) {
-  if (world > kMaxPeers || M % world) return -20;
+  if (world > kMaxPeers || (mode == COMM_AGB ? N % world : M % world)) return -20;
   const int bn = pick_bn(N, b_mn_major, 0);
   CUtensorMap ma, mb;
   int rc = make_map_2d(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, is_fp16);
@@ -564,8 +580,9 @@ extern "C" int epl_gemm_fused(int mode, const void* A, const void* B, int M, int
   p.accumulate = 0; p.out_dtype = is_fp16 ? EPL_F16 : EPL_BF16; p.a_mn_major = 0; p.b_mn_major = b_mn_major; p.alpha = 1.f;
   p.ab_format = is_fp16 ? 0 : 1;
   CommParams c{};
-  c.rank = rank; c.world = world; c.epoch = epoch; c.copy_ctas = copy_ctas; c.rows_per_rank = M / world;
-  c.local_sync = (uint32_t*)local_sync; c.ag_dst = const_cast<void*>(A); c.rs_out = rs_out;
+  c.rank = rank; c.world = world; c.epoch = epoch; c.copy_ctas = copy_ctas;
+  c.rows_per_rank = (mode == COMM_AGB ? N : M) / world;
+  c.local_sync = (uint32_t*)local_sync; c.ag_dst = const_cast<void*>(mode == COMM_AGB ? B : A); c.rs_out = rs_out;
   for (int i = 0; i < world; ++i) {
     c.flags[i] = (uint32_t*)flag_ptrs[i];
     c.ag_src[i] = ag_src ? ag_src[i] : nullptr;
@@ -577,6 +594,12 @@ extern "C" int epl_gemm_fused(int mode, const void* A, const void* B, int M, int
     if (bn == 256) return launch_gemm<256, COMM_AG>(ma, mb, p, c, kNumSMs, st);
     if (bn == 160) return launch_gemm<160, COMM_AG>(ma, mb, p, c, kNumSMs, st);
     return launch_gemm<128, COMM_AG>(ma, mb, p, c, kNumSMs, st);
+  }
+  if (mode == COMM_AGB) {
+    if (b_mn_major || ldb != K || (K % 8)) return -21;
+    if (bn == 256) return launch_gemm<256, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
+    if (bn == 160) return launch_gemm<160, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
+    return launch_gemm<128, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
   }
   if (mode == COMM_RS) {
     if (is_fp16 || (N % 8) || (ldd % 8)) return -21;

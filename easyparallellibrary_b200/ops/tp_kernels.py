@@ -113,3 +113,38 @@ def gemm_rs(a: torch.Tensor, w: torch.Tensor, group, b_mn_major: bool = False) -
                           stage.peer_table(0), out.data_ptr(), 0, _lib.stream())
   _lib.check(rc, "gemm_rs")
   return out
+
+
+def ag_weight_gemm(x2: torch.Tensor, w_shard: torch.Tensor, group, bias=None, gelu: bool = False):
+  """K2 — ZeRO-3 weight all-gather fused with the GEMM that consumes it.
+
+  ``w_shard``: this rank's ``[N/world, K]`` rows of the weight.  Returns ``(y, pre, w_full)`` with
+  ``y = x2 @ gather(w_shard)^T (+bias)(gelu)``; the gathered weight is kept for the backward GEMMs.
+  """
+  from easyparallellibrary_b200.ops import linear as L
+  lib = _lib_fused()
+  ws = workspace(group, x2.device)
+  if not hasattr(ws, "pad_agb"):
+    ws.pad_agb = SignalPad(1, group.ranks, x2.device, group=ws.pg)
+    ws.sync_agb = torch.zeros(16, dtype=torch.int32, device=x2.device)
+    ws.epoch_agb = 0
+    ws.wshard = None
+  rows, K = w_shard.shape
+  N = rows * group.size
+  M = x2.shape[0]
+  es = w_shard.element_size()
+  nbytes = rows * K * es
+  if ws.wshard is None or ws.wshard.nbytes < nbytes:
+    torch.cuda.synchronize(x2.device)
+    ws.wshard = SymmetricBuffer(max(nbytes, 1 << 20), group.ranks, x2.device, group=ws.pg)
+  ws.wshard.tensor(w_shard.dtype, rows * K).copy_(w_shard.reshape(-1))
+  w_full = torch.empty((N, K), dtype=w_shard.dtype, device=x2.device)
+  y = torch.empty((M, N), dtype=x2.dtype, device=x2.device)
+  pre = torch.empty_like(y) if gelu else None
+  epi = L.EPI_BIAS_GELU if gelu else (L.EPI_BIAS if bias is not None else L.EPI_NONE)
+  ws.epoch_agb += 1
+  rc = lib.epl_gemm_fused(3, x2.data_ptr(), w_full.data_ptr(), M, N, K, x2.stride(0), K, N, 0, _lib.ptr(bias), _lib.ptr(pre), epi,
+                          y.data_ptr(), group.rank, group.size, ws.epoch_agb, COPY_CTAS, ws.pad_agb.slot_table(0),
+                          ws.sync_agb.data_ptr(), ws.wshard.peer_table(0), None, None, int(x2.dtype == torch.float16), _lib.stream())
+  _lib.check(rc, "ag_weight_gemm")
+  return y, pre, w_full

@@ -151,6 +151,17 @@ def check_tp(dev, world, rank):
       z = tp_fused.gemm_rs(a, w, group)
       torch.cuda.synchronize()
       outs[fused] = (y.float(), z.float(), xf.float())
+    # K2: the gathered operand is the (ZeRO-3 sharded) weight
+    from easyparallellibrary_b200.ops import tp_kernels
+    wsh = w[rank * (N // world):(rank + 1) * (N // world)].contiguous()
+    y2, _, wfull = tp_kernels.ag_weight_gemm(a, wsh, group, bias=b, gelu=False)
+    torch.cuda.synchronize()
+    wref = group.comm.allgather(wsh)
+    yref = torch.nn.functional.linear(a.float(), wref.float(), b.float())
+    dw2 = (wfull.float() - wref.float()).abs().max().item()
+    dy2 = (y2.float() - yref).abs().max().item()
+    log("   K2 weight-gather GEMM: |w_full diff|=%.1e |y diff|=%.3e (ref max %.2f)" % (dw2, dy2, yref.abs().max().item()))
+    assert dw2 == 0.0 and dy2 < 0.02 * yref.abs().max().item() + 0.1
     dy = (outs[True][0] - outs[False][0]).abs().max().item()
     dz = (outs[True][1] - outs[False][1]).abs().max().item()
     dx = (outs[True][2] - outs[False][2]).abs().max().item()
@@ -159,7 +170,10 @@ def check_tp(dev, world, rank):
     assert dx == 0.0 and dy < 0.1 and dz < 0.02 * ref + 0.1
     for fused in (False, True):
       tp_fused.USE_FUSED = fused
-      for name, fn in (("ag_gemm", lambda: tp_fused.ag_gemm(xs, w, group, bias=b, gelu=True)), ("gemm_rs", lambda: tp_fused.gemm_rs(a, w, group))):
+      from easyparallellibrary_b200.ops import linear as LL
+      k2 = (lambda: tp_kernels.ag_weight_gemm(a, wsh, group, bias=b)) if fused else (lambda: LL.gemm(a, group.comm.allgather(wsh), bias=b, epilogue=LL.EPI_BIAS))
+      for name, fn in (("ag_gemm", lambda: tp_fused.ag_gemm(xs, w, group, bias=b, gelu=True)), ("gemm_rs", lambda: tp_fused.gemm_rs(a, w, group)),
+                       ("agw_gemm", k2)):
         for _ in range(3):
           fn()
         torch.cuda.synchronize(); dist.barrier()
@@ -171,9 +185,9 @@ def check_tp(dev, world, rank):
         t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         results[(T, K, N, name, fused)] = t.item()
-    for name in ("ag_gemm", "gemm_rs"):
+    for name in ("ag_gemm", "gemm_rs", "agw_gemm"):
       fl = 2.0 * T * K * N
-      nv = (world - 1) / world * T * (K if name == "ag_gemm" else N) * 2
+      nv = (world - 1) / world * (T * K if name == "ag_gemm" else (T * N if name == "gemm_rs" else N * K)) * 2
       log("  %-8s NCCL+GEMM %.3f ms | fused %.3f ms | speedup %.2fx | roofline max(gemm %.3f ms @1.4PF, nvlink %.3f ms @770GB/s)" % (
           name, results[(T, K, N, name, False)], results[(T, K, N, name, True)],
           results[(T, K, N, name, False)] / results[(T, K, N, name, True)], fl / 1.4e12, nv / 770e6))

@@ -12,7 +12,11 @@ import torch
 
 from easyparallellibrary_b200.ops import _lib
 
-_IMPL = "auto"      # "auto" | "epl" | "sdpa"
+import os
+
+# "auto" | "epl" | "sdpa".  The hand-written kernel becomes the default once validated on hardware
+# (EPL_ATTENTION=epl forces it, =sdpa forces the cuDNN reference path).
+_IMPL = os.environ.get("EPL_ATTENTION", "sdpa")
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, dropout_p: float = 0.0) -> torch.Tensor:

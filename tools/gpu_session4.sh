@@ -1,6 +1,7 @@
 #!/bin/bash
 # 1-GPU: validate attention kernels first (short timeouts), then new tests, bench, ncu of the top kernels
 mkdir -p gpurun_out
+export EPL_ATTENTION=epl
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 echo "== attention tests"; timeout -s KILL 240 python -m pytest tests/test_kernels_gpu.py -q -x -k "flash_attention" --timeout 60 2>&1 | tail -15 | tee gpurun_out/pytest_attn.log
 echo "== other new tests"; timeout -s KILL 400 python -m pytest tests/test_kernels_gpu.py -q -k "fork or layernorm or linear_and_mlp or gpt2" --timeout 120 2>&1 | tail -8 | tee gpurun_out/pytest_new.log

@@ -20,9 +20,23 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 
-def plan_buckets(nbytes: Sequence[int], dtypes: Sequence[object], max_splits: int) -> List[List[int]]:
-  """Return buckets as lists of indices into the input (order preserved inside a dtype)."""
+def plan_buckets(nbytes: Sequence[int], dtypes: Sequence[object], max_splits: int, use_native: bool = True) -> List[List[int]]:
+  """Return buckets as lists of indices into the input (order preserved inside a dtype).
+
+  The planning loop runs in the native runtime (``csrc/runtime.cpp: epl_plan_buckets``) when the library is
+  built; the Python body below is the reference implementation and the fallback (they are cross-checked in
+  ``tests/test_native_runtime.py``)."""
   n = len(nbytes)
+  if use_native and n > 1:
+    try:
+      from easyparallellibrary_b200.runtime import native
+      if native.available():
+        ids, table = [], {}
+        for dt in dtypes:
+          ids.append(table.setdefault(dt, len(table)))
+        return native.plan_buckets([int(b) for b in nbytes], ids, int(max_splits))
+    except Exception:  # pragma: no cover - fall back to the Python planner
+      pass
   if n == 0:
     return []
   if n == 1:
@@ -43,9 +57,12 @@ def plan_buckets(nbytes: Sequence[int], dtypes: Sequence[object], max_splits: in
   for g, k in zip(groups, budget):
     sizes = [nbytes[i] for i in g]
     nonzero = [s for s in sizes if s] or [1]
-    mean = sum(nonzero) / len(nonzero)
+    mean = float(sum(nonzero)) / len(nonzero)
     sizes = [s if s else mean for s in sizes]
-    limit = sum(sizes) if k == 1 else sum(sizes) / (k - 1)
+    tot = 0.0
+    for x in sizes:           # plain left-to-right accumulation (Python's sum() is compensated; the native planner is not)
+      tot += x
+    limit = tot if k == 1 else tot / (k - 1)
     cur: List[int] = []
     acc = 0.0
     for idx, s in zip(g, sizes):

@@ -39,6 +39,12 @@ class PipelineExecutor(object):
     self.module = trainer.stage_modules[self.stage]
     policy = trainer.config.pipeline.strategy
     self.program = S.build_stage_program(policy, self.stage, self.num_stages, self.M, prefetch=1)
+    try:      # the native runtime generates the same program; use it when built (cross-checked in the tests)
+      from easyparallellibrary_b200.runtime import native
+      if native.available():
+        self.program = [S.Instr(op, mb) for op, mb in native.schedule_stage(policy, self.stage, self.num_stages, self.M, 1)]
+    except Exception:  # pragma: no cover
+      pass
     # two process groups -> activations and activation-gradients travel on independent NCCL streams
     self.pg_fwd = dist.new_group()
     self.pg_bwd = dist.new_group()

@@ -116,11 +116,12 @@ def main():
   epl.init(epl.Config(conf))
   cfg = GPT2Config.named(args.model, num_pipeline_stages=stages, tie_embeddings=(stages == 1), n_positions=max(1024, args.seq))
   torch.manual_seed(1234)
-  if stages == 1:
-    with epl.replicate(device_count=1):
+  with torch.device(dev):                      # random-init weights directly on the GPU
+    if stages == 1:
+      with epl.replicate(device_count=1):
+        model = GPT2(cfg)
+    else:
       model = GPT2(cfg)
-  else:
-    model = GPT2(cfg)
   from easyparallellibrary_b200.models.gpt2 import lm_loss
   trainer = epl.Trainer(model, "adamw", lr=1e-4, weight_decay=0.01, baseline=(args.impl == "baseline"),
                         loss_fn=lm_loss if stages > 1 else None)

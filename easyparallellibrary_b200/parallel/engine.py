@@ -368,6 +368,7 @@ class Trainer(object):
     self._overlap = False
     self._first_micro_batch = True
     self._last_micro_batch = True
+    self._mean = True
     for s, flat in self.flats.items():
       for b in flat.buckets:
         for p, o in zip(b.params, b.offsets):
@@ -387,8 +388,11 @@ class Trainer(object):
         view.add_(p.grad)
         p.grad = view if view.dtype == p.dtype else None
     b.ready += 1
-    if self._overlap and self._last_micro_batch and b.ready == len(b.params):
-      self._launch_bucket_reduce(s, b)
+    if self._last_micro_batch and b.ready % len(b.params) == 0:
+      if self.fused is not None and self.fused.overlap and not self.plan.pipeline:
+        self.fused.launch_bucket_async(s, b.index, self._mean and not self.has_split)
+      elif self._overlap:
+        self._launch_bucket_reduce(s, b)
 
   # ================================================================== one step
   def step(self, *batch, **kwargs) -> StepOutput:
@@ -399,6 +403,7 @@ class Trainer(object):
     cfg = self.config
     M = cfg.pipeline.num_micro_batch
     mean = cfg.communication.gradients_reduce_method == constant.REDUCE_MEAN
+    self._mean = mean
     graph = Graph.get()
     graph.pop_collections()
     for flat in self.flats.values():

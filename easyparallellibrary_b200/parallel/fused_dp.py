@@ -35,7 +35,10 @@ class FusedDataParallel(object):
     self.local_sync: Dict[int, torch.Tensor] = {}
     self.epochs: Dict[Tuple[int, int], int] = {}
     self.side = torch.cuda.Stream(device=trainer.device, priority=-1)
-    self.blocks = 148
+    self.blocks = 148                 # after backward: the whole GPU
+    self.overlap_blocks = 32          # during backward: co-resident with the GEMM CTAs (no shared memory, 512 threads)
+    self.launched = set()
+    self.overlap = True
 
   @classmethod
   def maybe_create(cls, trainer) -> Optional["FusedDataParallel"]:
@@ -51,7 +54,20 @@ class FusedDataParallel(object):
       self.local_sync[s] = torch.zeros(2 * len(flat.buckets), dtype=torch.int32, device=trainer.device)
     return self
 
-  def launch_bucket(self, s: int, bi: int, mean: bool) -> None:
+  def launch_bucket_async(self, s: int, bi: int, mean: bool) -> None:
+    """Called from the gradient hook when the last gradient of a bucket has been produced: the fused kernel runs on
+    a side stream while backward continues.  Safe because its first action is a cross-GPU barrier: no rank's weights
+    are overwritten before every rank has finished the backward of the layers in this bucket."""
+    if (s, bi) in self.launched or s not in self.pads:
+      return
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    self.side.wait_event(ev)
+    with torch.cuda.stream(self.side):
+      self.launch_bucket(s, bi, mean, self.overlap_blocks)
+    self.launched.add((s, bi))
+
+  def launch_bucket(self, s: int, bi: int, mean: bool, blocks: int = 0) -> None:
     tr = self.trainer
     comm, flat = tr.dp_comms[s], tr.flats[s]
     b, opt = flat.buckets[bi], tr.optimizers[s][bi]
@@ -72,7 +88,7 @@ class FusedDataParallel(object):
         gbuf.peer_table(b.start * es), pbuf.peer_table(b.start * es), self.pads[s].slot_table(bi), sync.data_ptr(),
         opt.master.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), _lib.ptr(opt.decay_mask), lo, hi - lo, comm.rank,
         comm.size, self.epochs[key], _lib.dtype_code(b.dtype), h.lr, h.beta1, h.beta2, h.eps, h.weight_decay, scale,
-        inv_c1, inv_c2, self.blocks, _lib.stream())
+        inv_c1, inv_c2, blocks or self.blocks, _lib.stream())
     _lib.check(rc, "fused_rs_adam_ag")
 
   def reduce_and_apply(self, mean: bool):
@@ -82,5 +98,9 @@ class FusedDataParallel(object):
         tr._apply_group_library(s, mean)
         continue
       for bi in range(len(tr.flats[s].buckets) - 1, -1, -1):
-        self.launch_bucket(s, bi, mean and not tr.has_split)
+        if (s, bi) not in self.launched:
+          self.launch_bucket(s, bi, mean and not tr.has_split)
+    if self.launched:
+      torch.cuda.current_stream().wait_stream(self.side)
+      self.launched.clear()
     return False, None

@@ -81,7 +81,6 @@ class NativeBackend(object):
     return t
 
   def all_reduce_async(self, t: torch.Tensor, op: str = "sum"):
-    t.record_stream(self.stream)
     self._check(self.lib.epl_comm_all_reduce(self.handle, self._p(t), self._p(t), ctypes.c_int64(t.numel()),
                                              _NCCL_DT[t.dtype], _NCCL_OP[op], ctypes.c_void_p(self._cur())), "all_reduce")
     return self
@@ -188,5 +187,7 @@ class NativeBackend(object):
 
   def close(self) -> None:
     if getattr(self, "handle", None):
+      torch.cuda.synchronize(self.device)       # nothing may still be queued on the side stream when it is destroyed
+      self.stream = None
       self.lib.epl_comm_destroy(self.handle)
       self.handle = None

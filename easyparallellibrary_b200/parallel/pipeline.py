@@ -86,7 +86,10 @@ class PipelineExecutor(object):
     collected = []
     tr._first_micro_batch, tr._last_micro_batch = True, False
     n_back = 0
+    debug = bool(int(__import__("os").environ.get("EPL_PIPE_DEBUG", "0")))
     for ins in self.program:
+      if debug:
+        print("[pipe rank %d stage %d] %r" % (tr.plan.rank, self.stage, ins), flush=True)
       if ins.op == S.RECV_F:
         if self._shape_fwd is None:
           self._shape_fwd = self._recv_meta(self.prev, self.pg_fwd)

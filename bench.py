@@ -78,6 +78,9 @@ class ClockSampler(threading.Thread):
 
 def main():
   args = parse()
+  if os.environ.get("EPL_HANG_DUMP"):          # debugging aid: dump every Python stack if the run stalls
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ["EPL_HANG_DUMP"]), exit=True)
   if args.impl == "reference":
     print(json.dumps({"impl": "reference", "unavailable":
                       "reference is TensorFlow-1.15/Python<=3.8 only (setup.py imports tensorflow; csrc links TF libs); "

@@ -273,3 +273,43 @@ def test_flash_attention_packed(B, S, H, causal):
   g, gr = qkv.grad.float(), ref_in.grad
   for idx, name in enumerate(("dq", "dk", "dv")):
     _close(g[:, :, idx], gr[:, :, idx], 3e-2, 3e-2 * gr[:, :, idx].abs().max().item(), "attn " + name)
+
+
+def test_vocab_parallel_xent_kernel_modes():
+  """K4 on one GPU: split the classes into two shards, run the statistics / gradient kernels per shard and combine
+  exactly like the distributed op does; compare with the unsharded fp32 cross-entropy."""
+  from easyparallellibrary_b200.ops.tensor_parallel import _VocabParallelXent
+
+  class FakeComm:
+    size, rank = 1, 0
+
+  torch.manual_seed(0)
+  rows, V = 64, 4096
+  logits = (torch.randn(rows, V, device=DEV) * 2).bfloat16()
+  labels = torch.randint(0, V, (rows,), device=DEV)
+  ref_in = logits.float().requires_grad_()
+  ref = torch.nn.functional.cross_entropy(ref_in, labels, reduction="none")
+  ref.sum().backward()
+  half = V // 2
+  shards = [logits[:, :half].contiguous().requires_grad_(), logits[:, half:].contiguous().requires_grad_()]
+  lib = __import__("easyparallellibrary_b200.ops._lib", fromlist=["require"]).require()
+  from easyparallellibrary_b200.ops import _lib
+  stats = []
+  for i, sh in enumerate(shards):
+    st = torch.empty(rows, 3, dtype=torch.float32, device=DEV)
+    rc = lib.epl_xent(sh.data_ptr(), labels.data_ptr(), None, None, st.data_ptr(), None, rows, half, sh.stride(0), 1.0, -100, i * half, 1,
+                      _lib.BF16, _lib.stream())
+    assert rc == 0
+    stats.append(st)
+  allst = torch.stack(stats)
+  gmax = allst[:, :, 0].max(0).values
+  gsum = (allst[:, :, 1] * (allst[:, :, 0] - gmax).exp()).sum(0)
+  loss = gsum.log() + gmax - allst[:, :, 2].sum(0)
+  _close(loss, ref, 1e-2, 2e-2, "vocab-parallel loss")
+  gst = torch.stack([gmax, gsum], 1).contiguous()
+  for i, sh in enumerate(shards):
+    g = torch.empty_like(sh)
+    rc = lib.epl_xent(sh.data_ptr(), labels.data_ptr(), None, g.data_ptr(), None, gst.data_ptr(), rows, half, sh.stride(0), 1.0, -100,
+                      i * half, 2, _lib.BF16, _lib.stream())
+    assert rc == 0
+    _close(g, ref_in.grad[:, i * half:(i + 1) * half], 2e-2, 1e-4, "vocab-parallel grad shard %d" % i)

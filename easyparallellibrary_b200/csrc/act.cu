@@ -70,7 +70,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
   if (col < D) {
-    for (int r = blockIdx.y * 8 + threadIdx.y; r < rows; r += gridDim.y * 8) {
+    const int step = gridDim.y * 8;
+    int r = blockIdx.y * 8 + threadIdx.y;
+    for (; r + 3 * step < rows; r += 4 * step) {          // four independent 16-byte loads in flight per thread
+      Vec<T, E> v0 = ld_vec<T, E>(x + (size_t)r * D + col);
+      Vec<T, E> v1 = ld_vec<T, E>(x + (size_t)(r + step) * D + col);
+      Vec<T, E> v2 = ld_vec<T, E>(x + (size_t)(r + 2 * step) * D + col);
+      Vec<T, E> v3 = ld_vec<T, E>(x + (size_t)(r + 3 * step) * D + col);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] += (to_f32<T>(v0.v[e]) + to_f32<T>(v1.v[e])) + (to_f32<T>(v2.v[e]) + to_f32<T>(v3.v[e]));
+    }
+    for (; r < rows; r += step) {
       Vec<T, E> v = ld_vec<T, E>(x + (size_t)r * D + col);
 #pragma unroll
       for (int e = 0; e < E; ++e) acc[e] += to_f32<T>(v.v[e]);
@@ -151,7 +161,7 @@ extern "C" int epl_colsum(const void* x, void* out, void* scratch, int rows, int
   BY_DTYPE(dtype, {
     constexpr int E = 16 / sizeof(T);
     const int gx = (D + 32 * E - 1) / (32 * E);
-    dim3 block(32, 8), grid(gx, std::max(1, std::min((rows + 31) / 32, (2 * kNumSMs + gx - 1) / gx)));
+    dim3 block(32, 8), grid(gx, std::max(1, std::min((rows + 31) / 32, (8 * kNumSMs + gx - 1) / gx)));
     colsum_kernel<T><<<grid, block, 0, st>>>((const T*)x, (float*)scratch, rows, D);
     finish_colsum_kernel<T><<<(D + 255) / 256, 256, 0, st>>>((const float*)scratch, (T*)out, D, accumulate);
   });

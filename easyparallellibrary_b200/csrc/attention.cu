@@ -52,6 +52,57 @@ EPL_DEVICE void st_swizzled_chunk(unsigned char* base, int r, int c, const uint3
   *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// ---- softmax passes over one 128-column S tile of this thread's row (kMask: only tiles that touch the causal diagonal
+// or the sequence end pay for the compare + select) ----------------------------------------------------------------
+template <bool kMask>
+EPL_DEVICE float attn_row_max(uint32_t taddr, int limit) {
+  float mx = kNegBig;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + ch * 32, v);
+    tmem_ld_wait();
+    const int lim = limit - ch * 32;
+    float m0 = kNegBig, m1 = kNegBig, m2 = kNegBig, m3 = kNegBig;
+#pragma unroll
+    for (int t = 0; t < 32; t += 4) {
+      m0 = fmaxf(m0, (!kMask || t + 0 < lim) ? __uint_as_float(v[t + 0]) : kNegBig);
+      m1 = fmaxf(m1, (!kMask || t + 1 < lim) ? __uint_as_float(v[t + 1]) : kNegBig);
+      m2 = fmaxf(m2, (!kMask || t + 2 < lim) ? __uint_as_float(v[t + 2]) : kNegBig);
+      m3 = fmaxf(m3, (!kMask || t + 3 < lim) ? __uint_as_float(v[t + 3]) : kNegBig);
+    }
+    mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+  }
+  return mx;
+}
+
+template <bool kMask>
+EPL_DEVICE float attn_row_exp(uint32_t taddr, int limit, float c, float mc, unsigned char* p_smem, int r) {
+  float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + ch * 32, v);
+    tmem_ld_wait();
+    const int lim = limit - ch * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float e[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float x = exp2f(__uint_as_float(v[g * 8 + t]) * c - mc);
+        e[t] = (!kMask || g * 8 + t < lim) ? x : 0.f;
+      }
+      rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
+      uint32_t w[4];
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) w[q2] = pack_bf16x2(e[2 * q2], e[2 * q2 + 1]);
+      st_swizzled_chunk(p_smem, r, ch * 4 + g, w);
+    }
+  }
+  return (rs0 + rs1) + (rs2 + rs3);
+}
+
 struct AttnParams {
   int B, S, H;
   float scale;            // 1/sqrt(D)
@@ -164,23 +215,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
       tc_fence_after();
       const int k0 = j * kTile;
       const bool need_mask = (k0 + kTile > p.S) || (p.causal && j == qt);
+      // columns [0, limit) of this tile are visible to this query row (branch-free masking: one compare + select)
+      const int limit = need_mask ? min(p.S - k0, p.causal ? qidx - k0 + 1 : kTile) : kTile;
       // pass 1: row maximum
-      float mx = kNegBig;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_addr + ch * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float s = __uint_as_float(v[t]);
-          if (need_mask) {
-            const int kidx = k0 + ch * 32 + t;
-            if (kidx >= p.S || (p.causal && kidx > qidx)) s = kNegBig;
-          }
-          mx = fmaxf(mx, s);
-        }
-      }
+      const float mx = need_mask ? attn_row_max<true>(tmem_s + lane_addr, limit) : attn_row_max<false>(tmem_s + lane_addr, limit);
       const float m_new = fmaxf(m, mx);
       const float alpha = exp2f((m - m_new) * c);
       const float mc = m_new * c;
@@ -200,32 +238,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
 #pragma unroll
       for (int d = 0; d < kD; ++d) o[d] *= alpha;
       // pass 2: probabilities -> bf16 -> swizzled shared memory
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_addr + ch * 32, v);
-        tmem_ld_wait();
-        float pr[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float s = __uint_as_float(v[t]);
-          float e = exp2f(s * c - mc);
-          if (need_mask) {
-            const int kidx = k0 + ch * 32 + t;
-            if (kidx >= p.S || (p.causal && kidx > qidx)) e = 0.f;
-          }
-          pr[t] = e;
-          rowsum += e;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2(pr[g * 8 + 2 * e], pr[g * 8 + 2 * e + 1]);
-          st_swizzled_chunk(smem + FwdSmem::kP, r, ch * 4 + g, w);
-        }
-      }
+      const float rowsum = need_mask ? attn_row_exp<true>(tmem_s + lane_addr, limit, c, mc, smem + FwdSmem::kP, r)
+                                     : attn_row_exp<false>(tmem_s + lane_addr, limit, c, mc, smem + FwdSmem::kP, r);
       l = l * alpha + rowsum;
       m = m_new;
       tc_fence_before();
@@ -413,6 +427,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const float lse2 = q_ok ? p.lse[((size_t)b * p.H + h) * p.S + qidx] * kLog2e : 0.f;
       const float dlt = q_ok ? p.delta[((size_t)b * p.H + h) * p.S + qidx] : 0.f;
       const bool need_mask = (k0 + kTile > p.S) || (p.causal && i == kt) || !q_ok;
+      const int limit = !q_ok ? 0 : (need_mask ? min(p.S - k0, p.causal ? qidx - k0 + 1 : kTile) : kTile);
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
       if (n > 0) {
@@ -438,24 +453,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         tmem_ld_32x32(t_s + lane_addr + ch * 32, sv_);
         tmem_ld_32x32(t_dp + lane_addr + ch * 32, dpv);
         tmem_ld_wait();
-        float pr[32], ds[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float e = exp2f(__uint_as_float(sv_[t]) * c - lse2);
-          if (need_mask) {
-            const int kidx = k0 + ch * 32 + t;
-            if (!q_ok || kidx >= p.S || (p.causal && kidx > qidx)) e = 0.f;
-          }
-          pr[t] = e;
-          ds[t] = e * (__uint_as_float(dpv[t]) - dlt);
-        }
+        const int lim = limit - ch * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t w[4], w2[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            w[e] = pack_bf16x2(pr[g * 8 + 2 * e], pr[g * 8 + 2 * e + 1]);
-            w2[e] = pack_bf16x2(ds[g * 8 + 2 * e], ds[g * 8 + 2 * e + 1]);
+          for (int q2 = 0; q2 < 4; ++q2) {
+            const int t = g * 8 + 2 * q2;
+            float e0 = exp2f(__uint_as_float(sv_[t]) * c - lse2), e1 = exp2f(__uint_as_float(sv_[t + 1]) * c - lse2);
+            e0 = (t < lim) ? e0 : 0.f;
+            e1 = (t + 1 < lim) ? e1 : 0.f;
+            w[q2] = pack_bf16x2(e0, e1);
+            w2[q2] = pack_bf16x2(e0 * (__uint_as_float(dpv[t]) - dlt), e1 * (__uint_as_float(dpv[t + 1]) - dlt));
           }
           st_swizzled_chunk(smem + BwdSmem::kP, r, ch * 4 + g, w);
           st_swizzled_chunk(smem + BwdSmem::kDS, r, ch * 4 + g, w2);

@@ -521,6 +521,245 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
   return EPL_CHECK_LAUNCH();
 }
 
+
+// =================================================================================================================
+// 2-CTA variant: a CTA pair (cluster of 2, same TPC) computes one 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), so shared-memory fill traffic
+// per SM drops from 48 KB to 32 KB per k-block and B is read by the tensor cores from both SMs' shared memory.
+// The leader CTA (rank 0) issues the MMAs; completion is multicast to the barriers of both CTAs; both CTAs run their own
+// TMA producer and their own epilogue (each owns 128 accumulator rows in its own TMEM).
+// =================================================================================================================
+constexpr int kStages2 = 6;                         // 6 x (16 KB A + 16 KB B-half) = 192 KB
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address with the CTA-rank bit cleared -> leader CTA
+
+EPL_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+EPL_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int kCols> EPL_DEVICE void tmem_alloc2(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_result)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols> EPL_DEVICE void tmem_dealloc2(uint32_t tmem_addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_addr), "n"(kCols) : "memory");
+}
+EPL_DEVICE void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (when all previously issued MMAs are complete) on the barrier at this smem offset in BOTH CTAs of the pair
+EPL_DEVICE void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// TMA load into this CTA's shared memory, completion bytes reported to the LEADER CTA's barrier at the same offset
+EPL_DEVICE void tma_load_2d_2cta(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+EPL_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const GemmParams p) {
+  constexpr int BN = 256, BM2 = 256;
+  constexpr int kABytes = BLOCK_M * BLOCK_K * 2, kBBytes = (BN / 2) * BLOCK_K * 2, kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = 512;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* tmem_full = empty_bar + kStages2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int m_blocks = (p.M + BM2 - 1) / BM2;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }   // 4 epilogue warps x 2 CTAs
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc2<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int mb, nb;
+        tile_coords(tile, m_blocks, n_blocks, mb, nb);
+        const int m0 = mb * BM2 + (int)cta * BLOCK_M, n0 = nb * BN + (int)cta * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * kStageBytes;
+          unsigned char* sb = sa + kABytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);          // bytes of both CTAs land on the leader's barrier
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn_major) {
+            tma_load_2d_2cta(sa, &map_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d_2cta(sa + a * (BLOCK_K * 128), &map_a, &full_bar[stage], m0 + a * 64, k0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d_2cta(sb, &map_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < (BN / 2) / 64; ++a) tma_load_2d_2cta(sb + a * (BLOCK_K * 128), &map_b, &full_bar[stage], n0 + a * 64, k0);
+          }
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_f16(BM2, BN, p.ab_format, p.a_mn_major, p.b_mn_major);
+      const uint32_t a_lbo = p.a_mn_major ? BLOCK_K * 128 : 16, b_lbo = p.b_mn_major ? BLOCK_K * 128 : 16;
+      const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2, b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit_2cta(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc]);
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs, 128 rows each) ================================
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int mb, nb;
+      tile_coords(tile, m_blocks, n_blocks, mb, nb);
+      const int row = mb * BM2 + (int)cta * BLOCK_M + quarter * 32 + lane;
+      const int n0 = nb * BN;
+      const size_t out_es = p.out_dtype == EPL_F32 ? 4 : 2;
+      unsigned char* drow = reinterpret_cast<unsigned char*>(p.D) + (size_t)row * p.ldd * out_es;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (p.epilogue == EPI_BIAS || p.epilogue == EPI_BIAS_GELU || p.epilogue == EPI_BIAS_RESIDUAL) {
+            if (p.bias != nullptr) {
+              const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(b[j]);
+            }
+          }
+          if (p.epilogue == EPI_BIAS_GELU) {
+            if (p.pre != nullptr) {
+              __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(p.pre) + (size_t)row * p.ldd + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j + 8 <= p.N && (p.ldd & 7) == 0) {
+                  Vec<__nv_bfloat16, 8> o;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { o.v[e] = __float2bfloat16_rn(v[j + e]); v[j + e] = __bfloat162float(o.v[e]); }
+                  st_vec<__nv_bfloat16, 8>(prow + j, o);
+                } else {
+                  for (int e = 0; e < 8; ++e) if (col0 + j + e < p.N) {
+                    __nv_bfloat16 h = __float2bfloat16_rn(v[j + e]); prow[j + e] = h; v[j + e] = __bfloat162float(h);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+          } else if (p.epilogue == EPI_DGELU || p.epilogue == EPI_BIAS_RESIDUAL) {
+            const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float a8[8];
+              if (col0 + j + 8 <= p.N && (p.ldd & 7) == 0) {
+                Vec<__nv_bfloat16, 8> a = ld_vec<__nv_bfloat16, 8>(arow + j);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a8[e] = __bfloat162float(a.v[e]);
+              } else {
+                for (int e = 0; e < 8; ++e) a8[e] = (col0 + j + e < p.N) ? __bfloat162float(arow[j + e]) : 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                v[j + e] = (p.epilogue == EPI_DGELU) ? v[j + e] * gelu_grad_f(a8[e]) : v[j + e] + a8[e];
+            }
+          }
+          if (p.out_dtype == EPL_BF16) store_chunk<__nv_bfloat16>(p, drow, col0, v);
+          else if (p.out_dtype == EPL_F32) store_chunk<float>(p, drow, col0, v);
+          else store_chunk<__half>(p, drow, col0, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);          // the leader's MMA thread owns the accumulator hand-off
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2<kTmemCols>(tmem_base);
+  }
+}
+
+static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_sms, cudaStream_t st) {
+  constexpr int kSmem = kStages2 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  int clusters = std::min(tiles, num_sms / 2);
+  gemm2_tcgen05_kernel<<<clusters * 2, kGemmThreads, kSmem, st>>>(ma, mb, p);
+  return EPL_CHECK_LAUNCH();
+}
+
 static int pick_bn(int N, int b_mn_major, int forced) {
   if (forced == 128 || forced == 256 || (forced == 160 && !b_mn_major)) return forced;
   // measured on B200 (tools/gemm_bench.py): the 128x256 tile wins whenever N spans more than one narrow tile,
@@ -540,7 +779,19 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
                         int a_mn_major, int b_mn_major, const void* bias, void* pre, const void* aux, int epilogue,
                         int accumulate, int out_dtype, float alpha, int is_fp16, int force_bn, int num_sms, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const int bn = pick_bn(N, b_mn_major, force_bn);
+  if (force_bn == 512 && M >= 256 && N >= 256) {              // 2-CTA 256x256 kernel (cta_group::2)
+    CUtensorMap ma2, mb2;
+    int rc2 = !a_mn_major ? make_map_2d(&ma2, A, M, K, lda, BLOCK_K, BLOCK_M, is_fp16) : make_map_2d(&ma2, A, K, M, lda, 64, BLOCK_K, is_fp16);
+    if (rc2) return rc2;
+    rc2 = !b_mn_major ? make_map_2d(&mb2, B, N, K, ldb, BLOCK_K, 128, is_fp16) : make_map_2d(&mb2, B, K, N, ldb, 64, BLOCK_K, is_fp16);
+    if (rc2) return rc2;
+    GemmParams p2;
+    p2.M = M; p2.N = N; p2.K = K; p2.ldd = ldd; p2.D = D; p2.bias = bias; p2.pre = pre; p2.aux = aux; p2.epilogue = epilogue;
+    p2.accumulate = accumulate; p2.out_dtype = out_dtype; p2.a_mn_major = a_mn_major; p2.b_mn_major = b_mn_major; p2.alpha = alpha;
+    p2.ab_format = is_fp16 ? 0 : 1;
+    return launch_gemm2(ma2, mb2, p2, num_sms > 0 ? num_sms : kNumSMs, (cudaStream_t)stream);
+  }
+  const int bn = pick_bn(N, b_mn_major, force_bn == 512 ? 0 : force_bn);
   CUtensorMap ma, mb;
   int rc;
   if (!a_mn_major) rc = make_map_2d(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, is_fp16);

@@ -132,7 +132,7 @@ def test_gemm_layouts(M, N, K, layout):
   _close(out, ref, 1e-2, 1e-2 * math.sqrt(K), "gemm %s" % layout)
 
 
-@pytest.mark.parametrize("bn", [128, 160, 256])
+@pytest.mark.parametrize("bn", [128, 160, 256, 512])       # 512 = the 2-CTA (cta_group::2) 256x256 kernel
 def test_gemm_tile_widths_and_epilogues(bn):
   from easyparallellibrary_b200.ops import linear as L
   torch.manual_seed(1)
@@ -313,3 +313,26 @@ def test_vocab_parallel_xent_kernel_modes():
                       i * half, 2, _lib.BF16, _lib.stream())
     assert rc == 0
     _close(g, ref_in.grad[:, i * half:(i + 1) * half], 2e-2, 1e-4, "vocab-parallel grad shard %d" % i)
+
+
+@pytest.mark.parametrize("layout", ["nt", "nn", "tn"])
+@pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 1600, 1600), (8192, 6400, 1600), (300, 264, 200)])
+def test_gemm_two_cta_layouts(M, N, K, layout):
+  """cta_group::2 kernel on all three operand layouts incl. ragged edges."""
+  from easyparallellibrary_b200.ops import linear as L
+  torch.manual_seed(0)
+  M, N, K = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
+  L._FORCE_BN = 512
+  try:
+    if layout == "nt":
+      a, b = torch.randn(M, K, device=DEV).bfloat16(), torch.randn(N, K, device=DEV).bfloat16()
+      ref, out = a.float() @ b.float().t(), L.gemm(a, b)
+    elif layout == "nn":
+      a, b = torch.randn(M, K, device=DEV).bfloat16(), torch.randn(K, N, device=DEV).bfloat16()
+      ref, out = a.float() @ b.float(), L.gemm(a, b, b_mn_major=True)
+    else:
+      a, b = torch.randn(K, M, device=DEV).bfloat16(), torch.randn(K, N, device=DEV).bfloat16()
+      ref, out = a.float().t() @ b.float(), L.gemm(a, b, a_mn_major=True, b_mn_major=True)
+  finally:
+    L._FORCE_BN = 0
+  _close(out, ref, 1e-2, 1e-2 * math.sqrt(K), "2cta gemm %s" % layout)

@@ -100,23 +100,36 @@ norm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __re
     for (int e = 0; e < E; ++e) { accg[i][e] = 0.f; accb[i][e] = 0.f; gam[i][e] = vi < nvec ? to_f32<T>(g.v[e]) : 0.f; }
   }
   int buf = 0;
+  // software pipeline: the next row's x / dy vectors are requested before this row's reduction + barrier
+  Vec<T, E> nx[VPT], nd[VPT];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      int vi = threadIdx.x + i * kBwdThreads;
+      if (vi < nvec) {
+        nx[i] = ld_vec<T, E>(x + (size_t)row * D + vi * E);
+        nd[i] = ld_vec<T, E>(dy + (size_t)row * D + vi * E);
+      }
+    }
+  };
+  if ((int)blockIdx.x < rows) fetch(blockIdx.x);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const T* xr = x + (size_t)row * D;
-    const T* dyr = dy + (size_t)row * D;
     const float mean = kRms ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
+    Vec<T, E> cx[VPT], cd[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) { cx[i] = nx[i]; cd[i] = nd[i]; }
+    if (row + (int)gridDim.x < rows) fetch(row + gridDim.x);
     float xh[VPT][E], gd[VPT][E];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
       int vi = threadIdx.x + i * kBwdThreads;
       if (vi < nvec) {
-        Vec<T, E> xv = ld_vec<T, E>(xr + vi * E);
-        Vec<T, E> dv = ld_vec<T, E>(dyr + vi * E);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          float d = to_f32<T>(dv.v[e]);
-          xh[i][e] = (to_f32<T>(xv.v[e]) - mean) * rstd;
+          float d = to_f32<T>(cd[i].v[e]);
+          xh[i][e] = (to_f32<T>(cx[i].v[e]) - mean) * rstd;
           gd[i][e] = d * gam[i][e];
           s1 += gd[i][e];
           s2 += gd[i][e] * xh[i][e];

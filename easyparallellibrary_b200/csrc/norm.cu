@@ -102,24 +102,22 @@ norm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __re
   int buf = 0;
   // software pipeline: the next row's x / dy vectors are requested before this row's reduction + barrier
   Vec<T, E> nx[VPT], nd[VPT];
-  auto fetch = [&](int row) {
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      int vi = threadIdx.x + i * kBwdThreads;
-      if (vi < nvec) {
-        nx[i] = ld_vec<T, E>(x + (size_t)row * D + vi * E);
-        nd[i] = ld_vec<T, E>(dy + (size_t)row * D + vi * E);
-      }
-    }
-  };
-  if ((int)blockIdx.x < rows) fetch(blockIdx.x);
+#define EPL_NORM_FETCH(ROW)                                                        \
+  _Pragma("unroll") for (int i = 0; i < VPT; ++i) {                                \
+    int vi = threadIdx.x + i * kBwdThreads;                                        \
+    if (vi < nvec) {                                                               \
+      nx[i] = ld_vec<T, E>(x + (size_t)(ROW) * D + vi * E);                        \
+      nd[i] = ld_vec<T, E>(dy + (size_t)(ROW) * D + vi * E);                       \
+    }                                                                              \
+  }
+  if ((int)blockIdx.x < rows) { EPL_NORM_FETCH(blockIdx.x) }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const float mean = kRms ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
     Vec<T, E> cx[VPT], cd[VPT];
 #pragma unroll
     for (int i = 0; i < VPT; ++i) { cx[i] = nx[i]; cd[i] = nd[i]; }
-    if (row + (int)gridDim.x < rows) fetch(row + gridDim.x);
+    if (row + (int)gridDim.x < rows) { EPL_NORM_FETCH(row + gridDim.x) }
     float xh[VPT][E], gd[VPT][E];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll

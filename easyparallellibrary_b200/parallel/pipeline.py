@@ -23,6 +23,93 @@ _META_LEN = 10
 _DTYPES = [torch.float32, torch.bfloat16, torch.float16, torch.int64, torch.int32]
 
 
+class _TorchP2P(object):
+  """CPU / gloo transport: torch.distributed point-to-point on two process groups (one per direction)."""
+
+  def __init__(self, prev: Optional[int], nxt: Optional[int]):
+    self.prev, self.next = prev, nxt
+    self.pg_fwd = dist.new_group()
+    self.pg_bwd = dist.new_group()
+
+  def send_fwd(self, t):
+    return dist.isend(t, self.next, group=self.pg_fwd)
+
+  def recv_fwd(self, t):
+    return dist.irecv(t, self.prev, group=self.pg_fwd)
+
+  def send_bwd(self, t):
+    return dist.isend(t, self.prev, group=self.pg_bwd)
+
+  def recv_bwd(self, t):
+    return dist.irecv(t, self.next, group=self.pg_bwd)
+
+  def send_meta(self, meta):
+    dist.send(meta, self.next, group=self.pg_fwd)
+
+  def recv_meta(self, meta):
+    dist.recv(meta, self.prev, group=self.pg_fwd)
+
+
+class _EventHandle(object):
+  def __init__(self, ev):
+    self.ev = ev
+
+  def wait(self):
+    torch.cuda.current_stream().wait_event(self.ev)
+
+
+class _NativeP2P(object):
+  """GPU transport: the in-tree NCCL communicator (``csrc/communicator.cpp``), one 2-rank communicator — hence one
+  dedicated side stream — per neighbour and direction.  A receive posted early never blocks the host or an unrelated
+  transfer, and every transfer hands back its own event, so a compute instruction waits for exactly its tensor."""
+
+  def __init__(self, me: int, prev: Optional[int], nxt: Optional[int], device):
+    from easyparallellibrary_b200.communicators.native import NativeBackend
+    self.fwd_in = self.bwd_out = self.fwd_out = self.bwd_in = None
+    if prev is not None:          # lower pair first on every rank: creation order is deadlock free
+      self.fwd_in = NativeBackend([prev, me], device)
+      self.bwd_out = NativeBackend([prev, me], device)
+    if nxt is not None:
+      self.fwd_out = NativeBackend([me, nxt], device)
+      self.bwd_in = NativeBackend([me, nxt], device)
+    self._keep = []
+
+  @staticmethod
+  def _done(be):
+    ev = torch.cuda.Event()
+    ev.record(be.stream)
+    return _EventHandle(ev)
+
+  def send_fwd(self, t):
+    self._keep.append(t)
+    self.fwd_out.send(t, 1)
+    return self._done(self.fwd_out)
+
+  def recv_fwd(self, t):
+    self.fwd_in.recv(t, 0)
+    return self._done(self.fwd_in)
+
+  def send_bwd(self, t):
+    self._keep.append(t)
+    self.bwd_out.send(t, 0)
+    return self._done(self.bwd_out)
+
+  def recv_bwd(self, t):
+    self.bwd_in.recv(t, 1)
+    return self._done(self.bwd_in)
+
+  def send_meta(self, meta):
+    self.send_fwd(meta).wait()
+    torch.cuda.current_stream().synchronize()
+
+  def recv_meta(self, meta):
+    self.recv_fwd(meta).wait()
+    torch.cuda.current_stream().synchronize()
+
+  def flush(self):
+    self._keep.clear()
+
+
 class PipelineExecutor(object):
   def __init__(self, trainer):
     self.tr = trainer
@@ -45,9 +132,11 @@ class PipelineExecutor(object):
         self.program = [S.Instr(op, mb) for op, mb in native.schedule_stage(policy, self.stage, self.num_stages, self.M, 1)]
     except Exception:  # pragma: no cover
       pass
-    # two process groups -> activations and activation-gradients travel on independent NCCL streams
-    self.pg_fwd = dist.new_group()
-    self.pg_bwd = dist.new_group()
+    # activations and activation-gradients travel on independent streams / communicators
+    if trainer.device.type == "cuda":
+      self.p2p = _NativeP2P(plan.rank, self.prev, self.next, trainer.device)
+    else:
+      self.p2p = _TorchP2P(self.prev, self.next)
     # one group per model replica (all stages of that replica) for cross-stage reductions
     self.replica_group = None
     for r in range(plan.num_replicas):
@@ -60,17 +149,14 @@ class PipelineExecutor(object):
     self.device = trainer.device
 
   # ------------------------------------------------------------------ metadata handshake (first step only)
-  def _send_meta(self, t: torch.Tensor, dst: int, group) -> None:
-    meta = torch.zeros(_META_LEN, dtype=torch.int64, device=self.device)
-    meta[0] = t.dim()
-    meta[1] = _DTYPES.index(t.dtype)
-    for i, s in enumerate(t.shape):
-      meta[2 + i] = s
-    dist.send(meta, dst, group=group)
+  def _send_meta(self, t: torch.Tensor) -> None:
+    vals = [t.dim(), _DTYPES.index(t.dtype)] + list(t.shape)
+    meta = torch.tensor(vals + [0] * (_META_LEN - len(vals)), dtype=torch.int64, device=self.device)
+    self.p2p.send_meta(meta)
 
-  def _recv_meta(self, src: int, group) -> Tuple[torch.Size, torch.dtype]:
+  def _recv_meta(self) -> Tuple[torch.Size, torch.dtype]:
     meta = torch.zeros(_META_LEN, dtype=torch.int64, device=self.device)
-    dist.recv(meta, src, group=group)
+    self.p2p.recv_meta(meta)
     meta = meta.cpu().tolist()
     return torch.Size(meta[2:2 + meta[0]]), _DTYPES[meta[1]]
 
@@ -92,13 +178,13 @@ class PipelineExecutor(object):
         print("[pipe rank %d stage %d] %r" % (tr.plan.rank, self.stage, ins), flush=True)
       if ins.op == S.RECV_F:
         if self._shape_fwd is None:
-          self._shape_fwd = self._recv_meta(self.prev, self.pg_fwd)
+          self._shape_fwd = self._recv_meta()
         buf = torch.empty(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
-        recv_f[ins.mb] = (buf, dist.irecv(buf, self.prev, group=self.pg_fwd))
+        recv_f[ins.mb] = (buf, self.p2p.recv_fwd(buf))
       elif ins.op == S.RECV_B:
         out = outputs[ins.mb]
         buf = torch.empty_like(out)
-        recv_b[ins.mb] = (buf, dist.irecv(buf, self.next, group=self.pg_bwd))
+        recv_b[ins.mb] = (buf, self.p2p.recv_bwd(buf))
       elif ins.op == S.F:
         mb = micro[ins.mb]
         if self.first:
@@ -121,9 +207,9 @@ class PipelineExecutor(object):
       elif ins.op == S.SEND_F:
         y = outputs[ins.mb]
         if not getattr(self, "_meta_sent", False):
-          self._send_meta(y, self.next, self.pg_fwd)
+          self._send_meta(y)
           self._meta_sent = True
-        sends.append(dist.isend(y.detach(), self.next, group=self.pg_fwd))
+        sends.append(self.p2p.send_fwd(y.detach().contiguous()))
       elif ins.op == S.B:
         n_back += 1
         tr._last_micro_batch = n_back == self.M
@@ -138,11 +224,13 @@ class PipelineExecutor(object):
         tr._first_micro_batch = False
       elif ins.op == S.SEND_B:
         x = inputs.pop(ins.mb)
-        sends.append(dist.isend(x.grad, self.prev, group=self.pg_bwd))
+        sends.append(self.p2p.send_bwd(x.grad.contiguous()))
       # REDUCE / APPLY are executed by the trainer after the program
     for w in sends:
       w.wait()
     inputs.clear()
+    if hasattr(self.p2p, "flush"):
+      self.p2p.flush()
     # the loss lives on the last stage; share its mean with every stage of the replica
     stat = torch.zeros(1, device=self.device, dtype=torch.float32)
     if self.last and losses:
@@ -157,15 +245,15 @@ class PipelineExecutor(object):
       x = batch[0]
     else:
       if self._shape_fwd is None:
-        self._shape_fwd = self._recv_meta(self.prev, self.pg_fwd)
+        self._shape_fwd = self._recv_meta()
       x = torch.empty((batch[0].shape[0],) + tuple(self._shape_fwd[0][1:]), dtype=self._shape_fwd[1], device=self.device)
-      dist.recv(x, self.prev, group=self.pg_fwd)
+      self.p2p.recv_fwd(x).wait()
     y = self.module(x)
     if not self.last:
       if not getattr(self, "_meta_sent", False):
-        self._send_meta(y, self.next, self.pg_fwd)
+        self._send_meta(y)
         self._meta_sent = True
-      dist.send(y, self.next, group=self.pg_fwd)
+      self.p2p.send_fwd(y.contiguous()).wait()
       return None
     return self.tr.loss_fn(y, *batch[1:]) if self.tr.loss_fn is not None else y
 

@@ -20,7 +20,7 @@ from easyparallellibrary_b200.runtime import native
 _NCCL_DT = {torch.int8: 0, torch.uint8: 1, torch.int32: 2, torch.int64: 4, torch.float16: 6, torch.float32: 7,
             torch.float64: 8, torch.bfloat16: 9, torch.bool: 1}
 _NCCL_OP = {"sum": 0, "prod": 1, "max": 2, "min": 3, "avg": 4}
-_counter = [0]
+_counter = {}          # per rank-set creation counter: identical on every member of the set
 
 
 def _find_nccl() -> str:
@@ -44,8 +44,9 @@ class NativeBackend(object):
     me = dist.get_rank()
     self.rank = self.ranks.index(me)
     self.device = device
-    _counter[0] += 1
-    key = "epl_nccl_id/%s/%d" % ("-".join(map(str, self.ranks)), _counter[0])
+    rk = "-".join(map(str, self.ranks))
+    _counter[rk] = _counter.get(rk, 0) + 1
+    key = "epl_nccl_id/%s/%d" % (rk, _counter[rk])
     store = dist.distributed_c10d._get_default_store()
     ident = ctypes.create_string_buffer(128)
     if self.rank == 0:

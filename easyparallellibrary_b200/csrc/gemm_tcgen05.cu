@@ -82,7 +82,8 @@ struct SmemLayout {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 160 ? 5 : 4);
   static constexpr int kBarrierOffset = kStages * kStageBytes;
-  static constexpr int kTotalBytes = kBarrierOffset + 256 + 1024;   // barriers + alignment slack
+  static constexpr int kStagingOffset = kBarrierOffset + 256;       // 4 epilogue warps x 4 KB (reduce-scatter epilogue transposes here)
+  static constexpr int kTotalBytes = kStagingOffset + 16384 + 1024; // + alignment slack
 };
 
 // weight-gather order: all m-blocks of one n-block before the next n-block, starting with the n-blocks whose weights
@@ -167,7 +168,7 @@ EPL_DEVICE int rotate_mb(int mb, int m_blocks, const CommParams& c) {
 }
 
 // ---- copy role of the all-gather -> GEMM kernel: pull every rank's shard into the local gathered buffer ----------
-EPL_DEVICE void ag_copy_role(const GemmParams& p, const CommParams& c, int gemm_ctas) {
+EPL_DEVICE void ag_copy_role(const GemmParams& p, const CommParams& c, int gemm_ctas, unsigned char* copy_smem) {
   const int cid = blockIdx.x - gemm_ctas;
   if (cid == 0) {
     cross_gpu_signal_wait(c, 0);                       // every rank's shard is ready to be read
@@ -177,25 +178,54 @@ EPL_DEVICE void ag_copy_role(const GemmParams& p, const CommParams& c, int gemm_
     while (ld_acquire_gpu(c.local_sync) < c.epoch) {}
   }
   __syncthreads();
-  const size_t chunk_bytes = (size_t)c.rows_per_rank * p.K * 2;
-  const size_t vecs = chunk_bytes / 16;
-  const size_t per_cta = (vecs + c.copy_ctas - 1) / c.copy_ctas;
-  const size_t v0 = (size_t)cid * per_cta, v1 = min(vecs, v0 + per_cta);
-  for (int step = 0; step < c.world; ++step) {
-    const int src = (c.rank + step) % c.world;         // local chunk first, then ring order (spreads load over links)
-    const int4* from = reinterpret_cast<const int4*>(c.ag_src[src]);
-    int4* to = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(c.ag_dst) + (size_t)src * chunk_bytes);
-    size_t i = v0 + threadIdx.x;
-    for (; i + 3 * kGemmThreads < v1; i += 4 * kGemmThreads) {          // 4 x 16 B in flight per thread
-      int4 a = ld_stream(from + i), b = ld_stream(from + i + kGemmThreads);
-      int4 d = ld_stream(from + i + 2 * kGemmThreads), e = ld_stream(from + i + 3 * kGemmThreads);
-      to[i] = a; to[i + kGemmThreads] = b; to[i + 2 * kGemmThreads] = d; to[i + 3 * kGemmThreads] = e;
-    }
-    for (; i < v1; i += kGemmThreads) to[i] = ld_stream(from + i);
-    fence_proxy_async_all();                           // generic-proxy stores -> visible to the TMA (async proxy) reads
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); red_release_gpu_add(c.local_sync + 8 + src, 1u); }
+  // Bulk-DMA ring: one thread streams [peer global -> shared -> local global] with cp.async.bulk; kCopySlots x 32 KB are in
+  // flight per copy CTA, so a handful of CTAs keeps ~2.5 MB outstanding — enough to cover NVLink latency at full bandwidth
+  // without spending registers or issue slots on the copy (the 20 copy CTAs would otherwise top out near 150 GB/s).
+  constexpr int kCopySlots = 5;                           // 4 loads in flight + 1 slot draining (160 KB fits every tile config)
+  constexpr uint32_t kPiece = 32768;
+  uint64_t* cbar = reinterpret_cast<uint64_t*>(copy_smem + kCopySlots * kPiece);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCopySlots; ++i) mbar_init(&cbar[i], 1);
+    mbar_fence_init();
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const size_t chunk_bytes = (size_t)c.rows_per_rank * p.K * 2;
+    size_t per_cta = (chunk_bytes / c.copy_ctas + 15) & ~(size_t)15;
+    const size_t b0 = min((size_t)cid * per_cta, chunk_bytes), b1 = min(b0 + per_cta, chunk_bytes);
+    const int pieces = (int)((b1 - b0 + kPiece - 1) / kPiece);
+    uint32_t it = 0;                                      // global piece counter -> ring slot + phase
+    for (int step = 0; step < c.world; ++step) {
+      const int src = (c.rank + step) % c.world;          // local chunk first, then ring order
+      const unsigned char* from = reinterpret_cast<const unsigned char*>(c.ag_src[src]) + b0;
+      unsigned char* to = reinterpret_cast<unsigned char*>(c.ag_dst) + (size_t)src * chunk_bytes + b0;
+      for (int q = 0; q < pieces + kCopySlots - 2; ++q) {
+        if (q < pieces) {                                 // issue load q
+          const uint32_t slot = (it + q) % kCopySlots;
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the slot's previous store (two groups back) has drained
+          const uint32_t bytes = (uint32_t)min((size_t)kPiece, (b1 - b0) - (size_t)q * kPiece);
+          mbar_expect_tx(&cbar[slot], bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       :: "r"(smem_u32(copy_smem + slot * kPiece)), "l"(from + (size_t)q * kPiece), "r"(bytes), "r"(smem_u32(&cbar[slot])) : "memory");
+        }
+        const int d = q - (kCopySlots - 2);               // store piece d once its load has landed
+        if (d >= 0) {
+          const uint32_t slot = (it + d) % kCopySlots, ph = ((it + d) / kCopySlots) & 1;
+          mbar_wait(&cbar[slot], ph);
+          const uint32_t bytes = (uint32_t)min((size_t)kPiece, (b1 - b0) - (size_t)d * kPiece);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       :: "l"(to + (size_t)d * kPiece), "r"(smem_u32(copy_smem + slot * kPiece)), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      it += pieces;
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // this source's rows are in local memory
+      fence_proxy_async_all();
+      __threadfence();
+      red_release_gpu_add(c.local_sync + 8 + src, 1u);
+    }
+  }
+  __syncthreads();
   // end barrier: nobody may overwrite its shard before every peer has finished reading it
   __shared__ int last_copy;
   if (threadIdx.x == 0) last_copy = (atomicAdd(c.local_sync + 1, 1u) == (uint32_t)c.copy_ctas * c.epoch - 1u);
@@ -208,14 +238,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p, const CommParams c) {
   using L = SmemLayout<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const int gemm_ctas = (kComm == COMM_AG || kComm == COMM_AGB) ? (int)gridDim.x - c.copy_ctas : (int)gridDim.x;
   if constexpr (kComm == COMM_AG || kComm == COMM_AGB) {
-    if ((int)blockIdx.x >= gemm_ctas) { ag_copy_role(p, c, gemm_ctas); return; }
+    if ((int)blockIdx.x >= gemm_ctas) { ag_copy_role(p, c, gemm_ctas, smem); return; }
   }
   constexpr int kStages = L::kStages;
   constexpr int kTmemCols = 512;                       // 2 accumulator stages of BN (<= 256) fp32 columns
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
@@ -330,6 +360,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else {
     // ================================ epilogue (warps 2..5) =======================
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+    const CommParams& cm = c;                             // (the chunk loop below reuses the name `c`)
+    (void)cm;
     int acc = 0; uint32_t acc_phase = 0;
     bool rs_go = false;
     (void)rs_go;
@@ -409,9 +441,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 v[j + e] = (p.epilogue == EPI_DGELU) ? v[j + e] * gelu_grad_f(a8[e]) : v[j + e] + a8[e];
             }
           }
-          if (p.out_dtype == EPL_BF16) store_chunk<__nv_bfloat16>(p, drow, col0, v);
-          else if (p.out_dtype == EPL_F32) store_chunk<float>(p, drow, col0, v);
-          else store_chunk<__half>(p, drow, col0, v);
+          if constexpr (kComm != COMM_RS) {
+            if (p.out_dtype == EPL_BF16) store_chunk<__nv_bfloat16>(p, drow, col0, v);
+            else if (p.out_dtype == EPL_F32) store_chunk<float>(p, drow, col0, v);
+            else store_chunk<__half>(p, drow, col0, v);
+          } else {
+            // stage this row's 32 values (64 B) in the warp's shared-memory tile [32 rows x 128 B], 16-byte chunks XOR-swizzled
+            unsigned char* wrow = smem + L::kStagingOffset + (warp - 2) * 4096 + lane * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 w;
+              w.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); w.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+              w.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); w.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(wrow + ((((c & 1) * 4 + g) ^ (lane & 7)) << 4)) = w;
+            }
+          }
+        }
+        if constexpr (kComm == COMM_RS) {
+          // every second chunk (or the last one): the warp writes its 32 x 128 B tile with full 128-byte lines per row,
+          // 4 rows per instruction — NVLink sees whole cache lines instead of 32 scattered 16-byte packets
+          if ((c & 1) || c == BN / 32 - 1) {
+            __syncwarp();
+            const int cbase = n0 + (c & ~1) * 32;
+            const int row0 = mb * BLOCK_M + quarter * 32;
+            const unsigned char* wtile = smem + L::kStagingOffset + (warp - 2) * 4096;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int ri = it * 4 + (lane >> 3), ch = lane & 7;
+              const int grow = row0 + ri, col = cbase + ch * 8;
+              const bool have = (ch < 4) || (c & 1);                       // second half exists only after an odd chunk
+              if (have && grow < p.M && col + 8 <= p.N) {
+                const uint4 w = *reinterpret_cast<const uint4*>(wtile + ri * 128 + ((ch ^ (ri & 7)) << 4));
+                const int owner = min(grow / cm.rows_per_rank, cm.world - 1);
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(cm.rs_stage[owner]) +
+                                     ((size_t)cm.rank * cm.rows_per_rank + (grow - owner * cm.rows_per_rank)) * p.ldd + col;
+                *reinterpret_cast<uint4*>(dst) = w;
+              }
+            }
+            __syncwarp();
+          }
         }
       }
       tc_fence_before();

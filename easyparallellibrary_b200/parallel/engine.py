@@ -105,6 +105,12 @@ class Trainer(object):
     self.config = env.config
     self.model = model
     self.loss_fn = loss_fn
+    if not isinstance(optimizer, str):          # an optimizer description object (e.g. ops.AdamWeightDecayOptimizer)
+      extra = optimizer.trainer_kwargs(model)
+      no_decay = extra.pop("no_decay", no_decay)
+      extra.update(opt_kwargs)
+      opt_kwargs = extra
+      optimizer = optimizer.kind
     self.opt_kind = optimizer.lower()
     self.hyper = make_hyper(self.opt_kind, **opt_kwargs)
     self.max_grad_norm = max_grad_norm

@@ -325,12 +325,48 @@ struct BwdSmem {
   static constexpr int kDO = kQ + 2 * kTile * 128;       // 2 stages
   static constexpr int kP = kDO + 2 * kTile * 128;       // 32 KB
   static constexpr int kDS = kP + 2 * kTile * 128;       // 32 KB
-  static constexpr int kBar = kDS + 2 * kTile * 128;
+  static constexpr int kDQ = kDS + 2 * kTile * 128;      // 32 KB fp32 [128 rows][64] staging for the TMA reduce-add of dQ
+  static constexpr int kBar = kDQ + kTile * kD * 4;
   static constexpr int kTotal = kBar + 128;
 };
 
+// dQ tile (fp32, [128 x 64] plain row-major in shared memory) += into dq_acc[b, q0.., h*64..] with ONE TMA reduction
+EPL_DEVICE void tma_reduce_add_3d(const void* desc, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :: "l"(desc), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// one dQ tile: TMEM -> (x scale) -> shared staging -> TMA reduce-add.  Replaces 8192 scalar fp32 atomics per tile pair.
+EPL_DEVICE void flush_dq_tile(unsigned char* stage, uint32_t t_dq_lane, int r, int warp, int lane, float scale,
+                              const void* map_dq, int col0, int row0, int b) {
+  if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous reduce has read the staging tile
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // staging = two 128B-swizzled atoms of [128 rows x 32 fp32]; chunk g of row r lives at (g ^ (r & 7)) -> conflict-free stores
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_dq_lane + ch * 32, v);
+    tmem_ld_wait();
+    unsigned char* rowp = stage + ch * (kTile * 128) + r * 128;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float4 w = make_float4(__uint_as_float(v[g * 4 + 0]) * scale, __uint_as_float(v[g * 4 + 1]) * scale,
+                             __uint_as_float(v[g * 4 + 2]) * scale, __uint_as_float(v[g * 4 + 3]) * scale);
+      *reinterpret_cast<float4*>(rowp + ((g ^ (r & 7)) << 4)) = w;
+    }
+  }
+  fence_proxy_async();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (warp == 2 && lane == 0) {
+    tma_reduce_add_3d(map_dq, stage, col0, row0, b);
+    tma_reduce_add_3d(map_dq, stage + kTile * 128, col0 + 32, row0, b);
+    tma_store_commit();
+  }
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const AttnParams p) {
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                const __grid_constant__ CUtensorMap map_dq, const AttnParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBar);
   uint64_t* q_full = bar_kv + 1;       // [2]
@@ -434,18 +470,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         // dQ tile of the previous iteration -> fp32 accumulation buffer (also frees P / dS for rewriting)
         mbar_wait(dq_full, (n - 1) & 1);
         tc_fence_after();
-        const int qprev = (i - 1) * kTile + r;
-        float* dst = p.dq_acc + (((size_t)b * p.S + qprev) * p.H + h) * kD;
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_dq + lane_addr + ch * 32, v);
-          tmem_ld_wait();
-          if (qprev < p.S) {
-#pragma unroll
-            for (int t = 0; t < 32; ++t) atomicAdd(dst + ch * 32 + t, __uint_as_float(v[t]) * p.scale);
-          }
-        }
+        flush_dq_tile(smem + BwdSmem::kDQ, t_dq + lane_addr, r, warp, lane, p.scale, &map_dq, h * kD, (i - 1) * kTile, b);
       }
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
@@ -479,19 +504,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     {
       mbar_wait(dq_full, (n_q - 1) & 1);
       tc_fence_after();
-      const int qlast = (i_begin + n_q - 1) * kTile + r;
-      float* dst = p.dq_acc + (((size_t)b * p.S + qlast) * p.H + h) * kD;
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_dq + lane_addr + ch * 32, v);
-        tmem_ld_wait();
-        if (qlast < p.S) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) atomicAdd(dst + ch * 32 + t, __uint_as_float(v[t]) * p.scale);
-        }
-      }
+      flush_dq_tile(smem + BwdSmem::kDQ, t_dq + lane_addr, r, warp, lane, p.scale, &map_dq, h * kD, (i_begin + n_q - 1) * kTile, b);
     }
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reductions have landed
     // dK, dV of this key tile -> dqkv (row = key index)
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -542,6 +557,20 @@ static EncodeTiledFn attn_get_encode() {
   }
   return fn;
 }
+// fp32 [B, S, cols], box {32, 128, 1}, 128B swizzle (TMA reduce-add target for dQ)
+static int make_map_3d_f32(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t S, uint64_t cols) {
+  EncodeTiledFn enc = attn_get_encode();
+  if (!enc) return -10;
+  cuuint64_t dims[3] = {cols, S, B};
+  cuuint64_t strides[2] = {cols * 4, S * cols * 4};
+  cuuint32_t box[3] = {32, kTile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
 // [B, S, cols] bf16, box {64, 128, 1}
 static int make_map_3d(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t S, uint64_t cols) {
   EncodeTiledFn enc = attn_get_encode();
@@ -580,10 +609,12 @@ extern "C" int epl_attn_fwd(const void* qkv, void* out, void* lse, int B, int S,
 extern "C" int epl_attn_bwd(const void* qkv, const void* out, const void* d_out, const void* lse, void* delta, void* dq_acc,
                             void* dqkv, int B, int S, int H, float scale, int causal, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap map_qkv, map_do;
+  CUtensorMap map_qkv, map_do, map_dq;
   int rc = make_map_3d(&map_qkv, qkv, B, S, (uint64_t)3 * H * kD);
   if (rc) return rc;
   rc = make_map_3d(&map_do, d_out, B, S, (uint64_t)H * kD);
+  if (rc) return rc;
+  rc = make_map_3d_f32(&map_dq, dq_acc, B, S, (uint64_t)H * kD);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -598,7 +629,7 @@ extern "C" int epl_attn_bwd(const void* qkv, const void* out, const void* d_out,
   p.B = B; p.S = S; p.H = H; p.scale = scale; p.causal = causal; p.lse = (float*)const_cast<void*>(lse);
   p.delta = (const float*)delta; p.dq_acc = (float*)dq_acc; p.dqkv = (__nv_bfloat16*)dqkv;
   dim3 grid((S + kTile - 1) / kTile, H, B);
-  attn_bwd_kernel<<<grid, kAttnThreads, BwdSmem::kTotal, st>>>(map_qkv, map_do, p);
+  attn_bwd_kernel<<<grid, kAttnThreads, BwdSmem::kTotal, st>>>(map_qkv, map_do, map_dq, p);
   const int64_t chunks = (int64_t)B * S * H * (kD / 8);
   attn_dq_convert_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>((const float*)dq_acc, (__nv_bfloat16*)dqkv, (int64_t)B * S, H);
   return EPL_CHECK_LAUNCH();

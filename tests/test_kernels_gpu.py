@@ -336,3 +336,18 @@ def test_gemm_two_cta_layouts(M, N, K, layout):
   finally:
     L._FORCE_BN = 0
   _close(out, ref, 1e-2, 1e-2 * math.sqrt(K), "2cta gemm %s" % layout)
+
+
+def test_rope_kernel():
+  from easyparallellibrary_b200.ops.rope import apply_rope, rope_reference
+  torch.manual_seed(0)
+  qkv = torch.randn(2, 96, 3, 4, 64, device=DEV).bfloat16().requires_grad_()
+  out = apply_rope(qkv, 10000.0, 3)
+  ref_in = qkv.detach().float().requires_grad_()
+  ref = rope_reference(ref_in, 10000.0, 3)
+  _close(out, ref, 2e-2, 2e-2, "rope fwd")
+  g = torch.randn_like(out)
+  out.backward(g)
+  ref.backward(g.float())
+  _close(qkv.grad, ref_in.grad, 2e-2, 3e-2, "rope bwd")
+  assert torch.equal(out[:, :, 2], qkv[:, :, 2])          # V untouched

@@ -26,7 +26,6 @@ namespace epl {
 
 constexpr int kD = 64;                  // head dimension
 constexpr int kTile = 128;              // queries / keys per tile
-constexpr int kAttnThreads = 192;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNegBig = -1.0e30f;
 
@@ -52,53 +51,58 @@ EPL_DEVICE void st_swizzled_chunk(unsigned char* base, int r, int c, const uint3
   *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// ---- softmax passes over one 128-column S tile of this thread's row (kMask: only tiles that touch the causal diagonal
-// or the sequence end pay for the compare + select) ----------------------------------------------------------------
+EPL_DEVICE float ex2_approx(float x) {            // bare MUFU.EX2 (exp2f() adds a denormal-range rescale: 3 extra instructions)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+EPL_DEVICE void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+EPL_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- softmax passes over this thread's 64 columns (one half) of one S tile row.  kMask: only tiles that touch the causal
+// diagonal or the sequence end pay for the compare + select. -----------------------------------------------------------
 template <bool kMask>
-EPL_DEVICE float attn_row_max(uint32_t taddr, int limit) {
-  float mx = kNegBig;
-#pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + ch * 32, v);
-    tmem_ld_wait();
-    const int lim = limit - ch * 32;
-    float m0 = kNegBig, m1 = kNegBig, m2 = kNegBig, m3 = kNegBig;
+EPL_DEVICE float attn_half_max(const uint32_t (&v0)[32], const uint32_t (&v1)[32], int lim) {
+  float m0 = kNegBig, m1 = kNegBig, m2 = kNegBig, m3 = kNegBig;
 #pragma unroll
-    for (int t = 0; t < 32; t += 4) {
-      m0 = fmaxf(m0, (!kMask || t + 0 < lim) ? __uint_as_float(v[t + 0]) : kNegBig);
-      m1 = fmaxf(m1, (!kMask || t + 1 < lim) ? __uint_as_float(v[t + 1]) : kNegBig);
-      m2 = fmaxf(m2, (!kMask || t + 2 < lim) ? __uint_as_float(v[t + 2]) : kNegBig);
-      m3 = fmaxf(m3, (!kMask || t + 3 < lim) ? __uint_as_float(v[t + 3]) : kNegBig);
-    }
-    mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+  for (int t = 0; t < 32; t += 4) {
+    m0 = fmaxf(m0, (!kMask || t + 0 < lim) ? __uint_as_float(v0[t + 0]) : kNegBig);
+    m1 = fmaxf(m1, (!kMask || t + 1 < lim) ? __uint_as_float(v0[t + 1]) : kNegBig);
+    m2 = fmaxf(m2, (!kMask || t + 2 < lim) ? __uint_as_float(v0[t + 2]) : kNegBig);
+    m3 = fmaxf(m3, (!kMask || t + 3 < lim) ? __uint_as_float(v0[t + 3]) : kNegBig);
   }
-  return mx;
+#pragma unroll
+  for (int t = 0; t < 32; t += 4) {
+    m0 = fmaxf(m0, (!kMask || t + 32 < lim) ? __uint_as_float(v1[t + 0]) : kNegBig);
+    m1 = fmaxf(m1, (!kMask || t + 33 < lim) ? __uint_as_float(v1[t + 1]) : kNegBig);
+    m2 = fmaxf(m2, (!kMask || t + 34 < lim) ? __uint_as_float(v1[t + 2]) : kNegBig);
+    m3 = fmaxf(m3, (!kMask || t + 35 < lim) ? __uint_as_float(v1[t + 3]) : kNegBig);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+// 32 columns -> probabilities -> bf16 -> four 16-byte chunks of the swizzled P tile; returns their sum
 template <bool kMask>
-EPL_DEVICE float attn_row_exp(uint32_t taddr, int limit, float c, float mc, unsigned char* p_smem, int r) {
+EPL_DEVICE float attn_exp_32(const uint32_t (&v)[32], int lim, float c, float mc, unsigned char* p_smem, int r, int chunk0) {
   float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-#pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + ch * 32, v);
-    tmem_ld_wait();
-    const int lim = limit - ch * 32;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float e[8];
+  for (int g = 0; g < 4; ++g) {
+    float e[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float x = exp2f(__uint_as_float(v[g * 8 + t]) * c - mc);
-        e[t] = (!kMask || g * 8 + t < lim) ? x : 0.f;
-      }
-      rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
-      uint32_t w[4];
-#pragma unroll
-      for (int q2 = 0; q2 < 4; ++q2) w[q2] = pack_bf16x2(e[2 * q2], e[2 * q2 + 1]);
-      st_swizzled_chunk(p_smem, r, ch * 4 + g, w);
+    for (int t = 0; t < 8; ++t) {
+      const float x = ex2_approx(fmaf(__uint_as_float(v[g * 8 + t]), c, -mc));
+      e[t] = (!kMask || g * 8 + t < lim) ? x : 0.f;
     }
+    rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
+    uint32_t w[4];
+#pragma unroll
+    for (int q2 = 0; q2 < 4; ++q2) w[q2] = pack_bf16x2(e[2 * q2], e[2 * q2 + 1]);
+    st_swizzled_chunk(p_smem, r, chunk0 + g, w);
   }
   return (rs0 + rs1) + (rs2 + rs3);
 }
@@ -118,16 +122,23 @@ struct AttnParams {
 // ================================================================================================================
 // forward
 // ================================================================================================================
+constexpr int kFwdThreads = 320;      // warp 0: TMA, warp 1: MMA, warps 2-9: softmax (two warps per TMEM lane quarter)
+
 struct FwdSmem {
   static constexpr int kQ = 0;
   static constexpr int kK = kQ + kTile * 128;            // 2 stages
   static constexpr int kV = kK + 2 * kTile * 128;        // 2 stages
   static constexpr int kP = kV + 2 * kTile * 128;        // 32 KB
   static constexpr int kBar = kP + 2 * kTile * 128;
-  static constexpr int kTotal = kBar + 128;
+  static constexpr int kXm = kBar + 96;                  // bf16 [2 halves][128 rows]: row-max exchange between the two halves
+  static constexpr int kTotal = kXm + 2 * kTile * 2;     // 115296 B: two CTAs per SM
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+// Softmax thread layout: query row r = quarter*32 + lane is shared by TWO threads (warps w and w+4 address the same TMEM
+// lanes); thread `half` owns S columns [64*half, 64*half+64) and O columns [32*half, 32*half+32).  O accumulates in TMEM
+// across the whole key loop (tcgen05 accumulate) and is only touched by the softmax threads when the running maximum
+// moves by more than 2^8 (lazy rescale) — the common tile costs 2 TMEM loads, 64 max, 64 FFMA + 64 MUFU, 8 smem stores.
+__global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBar);
@@ -137,7 +148,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
   uint64_t* p_ready = s_full + 1;
   uint64_t* o_full = p_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = (p.S + kTile - 1) / kTile;
   const int qt = q_tiles - 1 - (int)blockIdx.x;          // heaviest (causal) tiles first
@@ -149,7 +159,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
     tma_prefetch_desc(&map_qkv);
     mbar_init(bar_q, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -174,7 +184,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(kTile, kTile, 1, 0, 0);      // S = Q K^T : both K-major
-      const uint32_t idesc_o = make_idesc_f16(kTile, kD, 1, 0, 1);         // O = P V   : A K-major, B (V) MN-major
+      const uint32_t idesc_o = make_idesc_f16(kTile, kD, 1, 0, 1);         // O += P V  : A K-major, B (V) MN-major
       const uint32_t sq = smem_u32(smem + FwdSmem::kQ), sp = smem_u32(smem + FwdSmem::kP);
       mbar_wait(bar_q, 0);
       for (int j = 0; j < n_kv; ++j) {
@@ -187,90 +197,107 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
         for (int k = 0; k < kD / 16; ++k)
           umma_f16(tmem_s, make_smem_desc_sw128(sq + k * 32, 16, 1024), make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
         umma_commit(s_full);
-        // O_t(j) = P(j) V(j) once the softmax warps have written P(j) (they have also drained O_t(j-1) by then)
+        // O += P(j) V(j) once the softmax warps have written P(j) (and rescaled O if the maximum moved)
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kTile / 16; ++kk) {
           const uint64_t da = make_smem_desc_sw128(sp + (kk >> 2) * (kTile * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, kTile * 128, 1024);
-          umma_f16(tmem_o, da, db, idesc_o, kk != 0);
+          umma_f16(tmem_o, da, db, idesc_o, (j | kk) != 0);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[s]);
       }
     }
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;                     // query row inside the tile
     const int qidx = q0 + r;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t my_s = tmem_s + lane_addr + half * 64, my_o = tmem_o + lane_addr + half * 32;
+    __nv_bfloat16* xm = reinterpret_cast<__nv_bfloat16*>(smem + FwdSmem::kXm);
     const float c = p.scale * kLog2e;
     float m = kNegBig, l = 0.f;
-    float o[kD];
-#pragma unroll
-    for (int d = 0; d < kD; ++d) o[d] = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(my_s, v0);
+      tmem_ld_32x32(my_s + 32, v1);
       const int k0 = j * kTile;
       const bool need_mask = (k0 + kTile > p.S) || (p.causal && j == qt);
-      // columns [0, limit) of this tile are visible to this query row (branch-free masking: one compare + select)
-      const int limit = need_mask ? min(p.S - k0, p.causal ? qidx - k0 + 1 : kTile) : kTile;
-      // pass 1: row maximum
-      const float mx = need_mask ? attn_row_max<true>(tmem_s + lane_addr, limit) : attn_row_max<false>(tmem_s + lane_addr, limit);
-      const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * c);
-      const float mc = m_new * c;
-      // the previous P V product must be folded into O before P is overwritten
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
+      // columns [0, lim) of this thread's half are visible to this query row (branch-free: one compare + select each)
+      const int lim = (need_mask ? min(p.S - k0, p.causal ? qidx - k0 + 1 : kTile) : kTile) - half * 64;
+      tmem_ld_wait();
+      float mx = need_mask ? attn_half_max<true>(v0, v1, lim) : attn_half_max<false>(v0, v1, lim);
+      // both halves must agree on the maximum bit for bit: exchange it rounded to bf16 (any value near the true maximum
+      // is a valid softmax offset)
+      const __nv_bfloat16 mxb = __float2bfloat16_rn(mx);
+      xm[half * kTile + r] = mxb;
+      asm volatile("bar.sync %0, 64;" :: "r"(1 + quarter) : "memory");
+      mx = fmaxf(__bfloat162float(mxb), __bfloat162float(xm[(half ^ 1) * kTile + r]));
+      // lazy rescale: keep the old offset unless the maximum grew by more than 2^8 (P stays <= 256, exact enough in
+      // bf16 / fp32 accumulation); the decision is made per warp because the TMEM accesses are warp-collective
+      const bool grow = (mx - m) * c > 8.f;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m;
+        const float alpha = ex2_approx((m - m_new) * c);
+        m = m_new;
+        l *= alpha;
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1);                  // P V(j-1) has landed in TMEM
+          tc_fence_after();
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {                 // 16 columns at a time: the S registers stay live across this
+            uint32_t o[16];
+            tmem_ld_32x16(my_o + ch * 16, o);
+            tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_o + lane_addr + ch * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) o[ch * 32 + t] += __uint_as_float(v[t]);
+            for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+            tmem_st_32x16(my_o + ch * 16, o);
+          }
+          tmem_st_wait();
         }
       }
-#pragma unroll
-      for (int d = 0; d < kD; ++d) o[d] *= alpha;
-      // pass 2: probabilities -> bf16 -> swizzled shared memory
-      const float rowsum = need_mask ? attn_row_exp<true>(tmem_s + lane_addr, limit, c, mc, smem + FwdSmem::kP, r)
-                                     : attn_row_exp<false>(tmem_s + lane_addr, limit, c, mc, smem + FwdSmem::kP, r);
-      l = l * alpha + rowsum;
-      m = m_new;
+      const float mc = m * c;
+      float rowsum;
+      if (need_mask) {
+        rowsum = attn_exp_32<true>(v0, lim, c, mc, smem + FwdSmem::kP, r, half * 8);
+        rowsum += attn_exp_32<true>(v1, lim - 32, c, mc, smem + FwdSmem::kP, r, half * 8 + 4);
+      } else {
+        rowsum = attn_exp_32<false>(v0, lim, c, mc, smem + FwdSmem::kP, r, half * 8);
+        rowsum += attn_exp_32<false>(v1, lim - 32, c, mc, smem + FwdSmem::kP, r, half * 8 + 4);
+      }
+      l += rowsum;
       tc_fence_before();
       fence_proxy_async();                                 // generic-proxy smem writes -> visible to the UMMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // last P V
+    // epilogue: O / l -> bf16.  P is dead once the last P V has completed, so its storage carries the row-sum exchange.
     mbar_wait(o_full, (n_kv - 1) & 1);
     tc_fence_after();
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_o + lane_addr + ch * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int t = 0; t < 32; ++t) o[ch * 32 + t] += __uint_as_float(v[t]);
-    }
+    float* xl = reinterpret_cast<float*>(smem + FwdSmem::kP);
+    xl[half * kTile + r] = l;
+    uint32_t o[32];
+    tmem_ld_32x32(my_o, o);
+    asm volatile("bar.sync %0, 64;" :: "r"(1 + quarter) : "memory");
+    l += xl[(half ^ 1) * kTile + r];
+    tmem_ld_wait();
     if (qidx < p.S) {
       const float inv = 1.f / l;
-      __nv_bfloat16* dst = p.out + (((size_t)b * p.S + qidx) * p.H + h) * kD;
+      __nv_bfloat16* dst = p.out + (((size_t)b * p.S + qidx) * p.H + h) * kD + half * 32;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 w;
-        w.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
-        w.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
-        w.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
-        w.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+        w.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(dst + g * 8) = w;
       }
-      p.lse[((size_t)b * p.H + h) * p.S + qidx] = m * p.scale + logf(l);
+      if (half == 0) p.lse[((size_t)b * p.H + h) * p.S + qidx] = m * p.scale + logf(l);
     }
   }
   tc_fence_before();
@@ -337,17 +364,17 @@ EPL_DEVICE void tma_reduce_add_3d(const void* desc, const void* smem_src, int c0
 }
 
 // one dQ tile: TMEM -> (x scale) -> shared staging -> TMA reduce-add.  Replaces 8192 scalar fp32 atomics per tile pair.
-EPL_DEVICE void flush_dq_tile(unsigned char* stage, uint32_t t_dq_lane, int r, int warp, int lane, float scale,
+// Called by all 256 compute threads; thread (row r, half) stages columns [32*half, 32*half+32).
+EPL_DEVICE void flush_dq_tile(unsigned char* stage, uint32_t t_dq_lane, int r, int half, bool issuer, float scale,
                               const void* map_dq, int col0, int row0, int b) {
-  if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous reduce has read the staging tile
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous reduce has read the staging tile
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   // staging = two 128B-swizzled atoms of [128 rows x 32 fp32]; chunk g of row r lives at (g ^ (r & 7)) -> conflict-free stores
-#pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
+  {
     uint32_t v[32];
-    tmem_ld_32x32(t_dq_lane + ch * 32, v);
+    tmem_ld_32x32(t_dq_lane + half * 32, v);
     tmem_ld_wait();
-    unsigned char* rowp = stage + ch * (kTile * 128) + r * 128;
+    unsigned char* rowp = stage + half * (kTile * 128) + r * 128;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       float4 w = make_float4(__uint_as_float(v[g * 4 + 0]) * scale, __uint_as_float(v[g * 4 + 1]) * scale,
@@ -356,15 +383,17 @@ EPL_DEVICE void flush_dq_tile(unsigned char* stage, uint32_t t_dq_lane, int r, i
     }
   }
   fence_proxy_async();
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (warp == 2 && lane == 0) {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (issuer) {
     tma_reduce_add_3d(map_dq, stage, col0, row0, b);
     tma_reduce_add_3d(map_dq, stage + kTile * 128, col0 + 32, row0, b);
     tma_store_commit();
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+constexpr int kBwdThreads = 320;      // warp 0: TMA, warp 1: MMA, warps 2-9: compute (two warps per TMEM lane quarter)
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_dq, const AttnParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -388,7 +417,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     tma_prefetch_desc(&map_qkv); tma_prefetch_desc(&map_do);
     mbar_init(bar_kv, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_ready, 4); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_ready, 8); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -452,8 +481,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       umma_commit(acc_full);
     }
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
+    const bool issuer = warp == 2 && lane == 0;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float c = p.scale * kLog2e;
     for (int n = 0; n < n_q; ++n) {
@@ -463,36 +493,39 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const float lse2 = q_ok ? p.lse[((size_t)b * p.H + h) * p.S + qidx] * kLog2e : 0.f;
       const float dlt = q_ok ? p.delta[((size_t)b * p.H + h) * p.S + qidx] : 0.f;
       const bool need_mask = (k0 + kTile > p.S) || (p.causal && i == kt) || !q_ok;
-      const int limit = !q_ok ? 0 : (need_mask ? min(p.S - k0, p.causal ? qidx - k0 + 1 : kTile) : kTile);
+      // columns [0, lim) of this thread's 64-column half are visible to this query row
+      const int lim0 = (!q_ok ? 0 : (need_mask ? min(p.S - k0, p.causal ? qidx - k0 + 1 : kTile) : kTile)) - half * 64;
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
       if (n > 0) {
         // dQ tile of the previous iteration -> fp32 accumulation buffer (also frees P / dS for rewriting)
         mbar_wait(dq_full, (n - 1) & 1);
         tc_fence_after();
-        flush_dq_tile(smem + BwdSmem::kDQ, t_dq + lane_addr, r, warp, lane, p.scale, &map_dq, h * kD, (i - 1) * kTile, b);
+        flush_dq_tile(smem + BwdSmem::kDQ, t_dq + lane_addr, r, half, issuer, p.scale, &map_dq, h * kD, (i - 1) * kTile, b);
       }
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < 2; ++ch) {
         uint32_t sv_[32], dpv[32];
-        tmem_ld_32x32(t_s + lane_addr + ch * 32, sv_);
-        tmem_ld_32x32(t_dp + lane_addr + ch * 32, dpv);
+        tmem_ld_32x32(t_s + lane_addr + half * 64 + ch * 32, sv_);
+        tmem_ld_32x32(t_dp + lane_addr + half * 64 + ch * 32, dpv);
         tmem_ld_wait();
-        const int lim = limit - ch * 32;
+        const int lim = lim0 - ch * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t w[4], w2[4];
 #pragma unroll
           for (int q2 = 0; q2 < 4; ++q2) {
             const int t = g * 8 + 2 * q2;
-            float e0 = exp2f(__uint_as_float(sv_[t]) * c - lse2), e1 = exp2f(__uint_as_float(sv_[t + 1]) * c - lse2);
-            e0 = (t < lim) ? e0 : 0.f;
-            e1 = (t + 1 < lim) ? e1 : 0.f;
+            float e0 = ex2_approx(fmaf(__uint_as_float(sv_[t]), c, -lse2)), e1 = ex2_approx(fmaf(__uint_as_float(sv_[t + 1]), c, -lse2));
+            if (need_mask) {
+              e0 = (t < lim) ? e0 : 0.f;
+              e1 = (t + 1 < lim) ? e1 : 0.f;
+            }
             w[q2] = pack_bf16x2(e0, e1);
             w2[q2] = pack_bf16x2(e0 * (__uint_as_float(dpv[t]) - dlt), e1 * (__uint_as_float(dpv[t + 1]) - dlt));
           }
-          st_swizzled_chunk(smem + BwdSmem::kP, r, ch * 4 + g, w);
-          st_swizzled_chunk(smem + BwdSmem::kDS, r, ch * 4 + g, w2);
+          st_swizzled_chunk(smem + BwdSmem::kP, r, half * 8 + ch * 4 + g, w);
+          st_swizzled_chunk(smem + BwdSmem::kDS, r, half * 8 + ch * 4 + g, w2);
         }
       }
       tc_fence_before();
@@ -504,18 +537,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     {
       mbar_wait(dq_full, (n_q - 1) & 1);
       tc_fence_after();
-      flush_dq_tile(smem + BwdSmem::kDQ, t_dq + lane_addr, r, warp, lane, p.scale, &map_dq, h * kD, (i_begin + n_q - 1) * kTile, b);
+      flush_dq_tile(smem + BwdSmem::kDQ, t_dq + lane_addr, r, half, issuer, p.scale, &map_dq, h * kD, (i_begin + n_q - 1) * kTile, b);
     }
-    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reductions have landed
-    // dK, dV of this key tile -> dqkv (row = key index)
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reductions have landed
+    // dK, dV of this key tile -> dqkv (row = key index): half 0 writes dV (slot 2), half 1 writes dK (slot 1)
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int kidx = k0 + r;
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {            // 0: dV (slot 2), 1: dK (slot 1)
-      const uint32_t src = which == 0 ? t_dv : t_dk;
-      const float mul = which == 0 ? 1.f : p.scale;
-      __nv_bfloat16* dst = p.dqkv + ((((size_t)b * p.S + kidx) * 3 + (which == 0 ? 2 : 1)) * p.H + h) * kD;
+    {
+      const uint32_t src = half == 0 ? t_dv : t_dk;
+      const float mul = half == 0 ? 1.f : p.scale;
+      __nv_bfloat16* dst = p.dqkv + ((((size_t)b * p.S + kidx) * 3 + (half == 0 ? 2 : 1)) * p.H + h) * kD;
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t v[32];
@@ -601,7 +633,7 @@ extern "C" int epl_attn_fwd(const void* qkv, void* out, void* lse, int B, int S,
   AttnParams p{};
   p.B = B; p.S = S; p.H = H; p.scale = scale; p.causal = causal; p.out = (__nv_bfloat16*)out; p.lse = (float*)lse;
   dim3 grid((S + kTile - 1) / kTile, H, B);
-  attn_fwd_kernel<<<grid, kAttnThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(map, p);
+  attn_fwd_kernel<<<grid, kFwdThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(map, p);
   return EPL_CHECK_LAUNCH();
 }
 
@@ -629,7 +661,7 @@ extern "C" int epl_attn_bwd(const void* qkv, const void* out, const void* d_out,
   p.B = B; p.S = S; p.H = H; p.scale = scale; p.causal = causal; p.lse = (float*)const_cast<void*>(lse);
   p.delta = (const float*)delta; p.dq_acc = (float*)dq_acc; p.dqkv = (__nv_bfloat16*)dqkv;
   dim3 grid((S + kTile - 1) / kTile, H, B);
-  attn_bwd_kernel<<<grid, kAttnThreads, BwdSmem::kTotal, st>>>(map_qkv, map_do, map_dq, p);
+  attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, st>>>(map_qkv, map_do, map_dq, p);
   const int64_t chunks = (int64_t)B * S * H * (kD / 8);
   attn_dq_convert_kernel<<<(int)((chunks + 255) / 256), 256, 0, st>>>((const float*)dq_acc, (__nv_bfloat16*)dqkv, (int64_t)B * S, H);
   return EPL_CHECK_LAUNCH();

@@ -73,6 +73,20 @@ class _NativeP2P(object):
       self.fwd_out = NativeBackend([me, nxt], device)
       self.bwd_in = NativeBackend([me, nxt], device)
     self._keep = []
+    # NCCL connects a send/recv pair lazily, on the HOST, inside the first call, and that call blocks until the peer
+    # makes the matching one.  Under 1F1B the first RECV_B of a stage is posted long before its neighbour reaches the
+    # matching SEND_B, so a lazy connect deadlocks the schedule (seen on B200: stage 0 inside ncclRecv, stage 1 waiting
+    # for stage 0's next activation).  Connect every channel here, in chain order, with one tiny transfer each.
+    probe = torch.zeros(8, dtype=torch.float32, device=device)
+    if prev is not None:
+      self.fwd_in.recv(probe, 0)
+      self.bwd_out.send(probe, 0)
+    if nxt is not None:
+      self.fwd_out.send(probe, 1)
+      self.bwd_in.recv(probe, 1)
+    for be in (self.fwd_in, self.bwd_out, self.fwd_out, self.bwd_in):
+      if be is not None:
+        be.stream.synchronize()
 
   @staticmethod
   def _done(be):

@@ -41,6 +41,7 @@ def parse():
   ap.add_argument("--zero", default="")
   ap.add_argument("--gc", default="")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--profile", default="", help="write a per-kernel GPU time table of 2 extra steps to this file")
   return ap.parse_args()
 
 
@@ -172,6 +173,33 @@ def main():
     return float(t.item()), out, clocks, _lib.launches - l0
 
   run(max(args.warmup, 3), False)
+  if args.profile:                               # kernel timeline of 2 steps (CUPTI via torch.profiler); never a bench value
+    from torch.profiler import profile, ProfilerActivity
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+      run(2, False)
+      torch.cuda.synchronize()
+    if rank == 0:
+      evs = [e for e in prof.events() if e.device_type.name == "CUDA"]
+      span = (max(e.time_range.end for e in evs) - min(e.time_range.start for e in evs)) / 1e3
+      agg = {}
+      for e in evs:
+        a = agg.setdefault(e.name, [0.0, 0])
+        a[0] += e.time_range.elapsed_us() / 1e3
+        a[1] += 1
+      busy = sum(v[0] for v in agg.values())
+      with open(args.profile, "w") as f:
+        f.write("2 steps: GPU span %.2f ms, sum of kernel time %.2f ms (%.1f%% busy, streams may overlap), %d kernels\n" % (
+            span, busy, 100.0 * busy / span, sum(v[1] for v in agg.values())))
+        for name, (ms_k, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+          f.write("%6.2f%% %9.3f ms %6d  %s\n" % (100.0 * ms_k / busy, ms_k, n, name[:110]))
+        # GEMM durations in launch order (first profiled step): 48 x [qkv, proj, fc1, fc2] forward, lm_head, then backward
+        gem = sorted((e.time_range.start, e.time_range.elapsed_us()) for e in evs if "gemm" in e.name)
+        gem = gem[:len(gem) // 2]
+        f.write("\nGEMM kernel durations (us) in launch order, step 1:\n")
+        for i in range(0, len(gem), 12):
+          f.write(" ".join("%6.0f" % d for _, d in gem[i:i + 12]) + "\n")
+    barrier()
   ms, out, clocks, launches = timed(args.steps, False)
   dp_replicas = trainer.plan.num_replicas
   tokens_per_step = args.batch * args.seq * (M if stages > 1 else 1) * dp_replicas

@@ -117,6 +117,7 @@ struct AttnParams {
   const float* delta;     // [B,H,S]  rowsum(dO * O)
   float* dq_acc;          // [B,S,H,64] fp32, zero on entry
   __nv_bfloat16* dqkv;    // [B,S,3,H,64]
+  long long* dbg;         // optional phase timestamps of CTA (0,0,0): [step][8] softmax warp 2, [64 + step][8] MMA thread
 };
 
 // ================================================================================================================
@@ -187,19 +188,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
       const uint32_t idesc_o = make_idesc_f16(kTile, kD, 1, 0, 1);         // O += P V  : A K-major, B (V) MN-major
       const uint32_t sq = smem_u32(smem + FwdSmem::kQ), sp = smem_u32(smem + FwdSmem::kP);
       mbar_wait(bar_q, 0);
+      const bool stamp = p.dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t sk = smem_u32(smem + FwdSmem::kK + s * kTile * 128), sv = smem_u32(smem + FwdSmem::kV + s * kTile * 128);
+        if (stamp) p.dbg[(64 + j) * 8 + 0] = clock64();
         mbar_wait(&kv_full[s], (j >> 1) & 1);
         tc_fence_after();
+        if (stamp) p.dbg[(64 + j) * 8 + 1] = clock64();
         // S(j) = Q K(j)^T.  (S(j-1) has been consumed: p_ready(j-1) was awaited before P V(j-1) was issued.)
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k)
           umma_f16(tmem_s, make_smem_desc_sw128(sq + k * 32, 16, 1024), make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
         umma_commit(s_full);
+        if (stamp) p.dbg[(64 + j) * 8 + 2] = clock64();
         // O += P(j) V(j) once the softmax warps have written P(j) (and rescaled O if the maximum moved)
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
+        if (stamp) p.dbg[(64 + j) * 8 + 3] = clock64();
 #pragma unroll
         for (int kk = 0; kk < kTile / 16; ++kk) {
           const uint64_t da = make_smem_desc_sw128(sp + (kk >> 2) * (kTile * 128) + (kk & 3) * 32, 16, 1024);
@@ -208,6 +214,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[s]);
+        if (stamp) p.dbg[(64 + j) * 8 + 4] = clock64();
       }
     }
   } else {
@@ -219,9 +226,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
     __nv_bfloat16* xm = reinterpret_cast<__nv_bfloat16*>(smem + FwdSmem::kXm);
     const float c = p.scale * kLog2e;
     float m = kNegBig, l = 0.f;
+    const bool stamp = p.dbg != nullptr && warp == 2 && lane == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
     for (int j = 0; j < n_kv; ++j) {
+      if (stamp) p.dbg[j * 8 + 0] = clock64();
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      if (stamp) p.dbg[j * 8 + 1] = clock64();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(my_s, v0);
       tmem_ld_32x32(my_s + 32, v1);
@@ -230,6 +240,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
       // columns [0, lim) of this thread's half are visible to this query row (branch-free: one compare + select each)
       const int lim = (need_mask ? min(p.S - k0, p.causal ? qidx - k0 + 1 : kTile) : kTile) - half * 64;
       tmem_ld_wait();
+      if (stamp) p.dbg[j * 8 + 2] = clock64();
       float mx = need_mask ? attn_half_max<true>(v0, v1, lim) : attn_half_max<false>(v0, v1, lim);
       // both halves must agree on the maximum bit for bit: exchange it rounded to bf16 (any value near the true maximum
       // is a valid softmax offset)
@@ -239,6 +250,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
       mx = fmaxf(__bfloat162float(mxb), __bfloat162float(xm[(half ^ 1) * kTile + r]));
       // lazy rescale: keep the old offset unless the maximum grew by more than 2^8 (P stays <= 256, exact enough in
       // bf16 / fp32 accumulation); the decision is made per warp because the TMEM accesses are warp-collective
+      if (stamp) p.dbg[j * 8 + 3] = clock64();
       const bool grow = (mx - m) * c > 8.f;
       if (__any_sync(0xffffffffu, grow)) {
         const float m_new = grow ? mx : m;
@@ -261,6 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
         }
       }
       const float mc = m * c;
+      if (stamp) p.dbg[j * 8 + 4] = clock64();
       float rowsum;
       if (need_mask) {
         rowsum = attn_exp_32<true>(v0, lim, c, mc, smem + FwdSmem::kP, r, half * 8);
@@ -270,10 +283,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
         rowsum += attn_exp_32<false>(v1, lim - 32, c, mc, smem + FwdSmem::kP, r, half * 8 + 4);
       }
       l += rowsum;
+      if (stamp) p.dbg[j * 8 + 5] = clock64();
       tc_fence_before();
       fence_proxy_async();                                 // generic-proxy smem writes -> visible to the UMMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
+      if (stamp) p.dbg[j * 8 + 6] = clock64();
     }
     // epilogue: O / l -> bf16.  P is dead once the last P V has completed, so its storage carries the row-sum exchange.
     mbar_wait(o_full, (n_kv - 1) & 1);
@@ -620,6 +635,9 @@ static int make_map_3d(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t S
 }  // namespace epl
 using namespace epl;
 
+static long long* g_attn_dbg = nullptr;
+extern "C" void epl_attn_set_debug(void* ptr) { g_attn_dbg = (long long*)ptr; }
+
 extern "C" int epl_attn_fwd(const void* qkv, void* out, void* lse, int B, int S, int H, float scale, int causal, void* stream) {
   CUtensorMap map;
   int rc = make_map_3d(&map, qkv, B, S, (uint64_t)3 * H * kD);
@@ -631,7 +649,7 @@ extern "C" int epl_attn_fwd(const void* qkv, void* out, void* lse, int B, int S,
     configured = true;
   }
   AttnParams p{};
-  p.B = B; p.S = S; p.H = H; p.scale = scale; p.causal = causal; p.out = (__nv_bfloat16*)out; p.lse = (float*)lse;
+  p.B = B; p.S = S; p.H = H; p.scale = scale; p.causal = causal; p.out = (__nv_bfloat16*)out; p.lse = (float*)lse; p.dbg = g_attn_dbg;
   dim3 grid((S + kTile - 1) / kTile, H, B);
   attn_fwd_kernel<<<grid, kFwdThreads, FwdSmem::kTotal, (cudaStream_t)stream>>>(map, p);
   return EPL_CHECK_LAUNCH();

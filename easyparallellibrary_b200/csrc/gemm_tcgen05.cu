@@ -65,14 +65,27 @@ struct CommParams {
   void* rs_out;                    // mode 2: local reduced output [rows_per_rank, ldd]
 };
 
+// tanh-approximation GELU on the MUFU tanh unit (abs error ~2^-11, below bf16 resolution): 6 / 9 FMA-pipe instructions
+// per element.  tanhf() costs ~25 and made the fused GELU epilogues slower than the main loop they hide behind.
+EPL_DEVICE float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 EPL_DEVICE float gelu_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(x2, k01, k0));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 EPL_DEVICE float gelu_grad_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float t = tanhf(k0 * (x + k1 * x * x * x));
-  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x * x);
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(x2, k01, k0));
+  const float du = fmaf(x2, 3.f * k01, k0);
+  const float sech2 = fmaf(-t, t, 1.f);
+  return fmaf(0.5f * x * sech2, du, fmaf(0.5f, t, 0.5f));
 }
 
 template <int BN>
@@ -634,7 +647,111 @@ EPL_DEVICE void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+constexpr int kGemm2Threads = 320;    // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quarter, 128 columns each)
+
+EPL_DEVICE uint4 ld_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+EPL_DEVICE void red_add_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// 32 accumulator columns of one output row -> epilogue math -> global.  `ax` = the matching 32 bf16 of the aux operand
+// (pre-activation for EPI_DGELU, residual for EPI_BIAS_RESIDUAL), prefetched by the caller BEFORE it waited for the
+// accumulator so the load latency hides behind the main loop; kFast = the whole chunk is in range and rows are 16-byte
+// aligned (everything except the ragged last N tile).
+template <bool kFast>
+EPL_DEVICE void epilogue_chunk32(const GemmParams& p, int row, int col0, const uint32_t (&r)[32], const uint4 (&ax)[4]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  if (p.bias != nullptr && (p.epilogue == EPI_BIAS || p.epilogue == EPI_BIAS_GELU || p.epilogue == EPI_BIAS_RESIDUAL)) {
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+    if (kFast) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint4 bv = *reinterpret_cast<const uint4*>(b + g * 8);          // warp-uniform address: one broadcast load
+        const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(w[e]); v[g * 8 + 2 * e] += f.x; v[g * 8 + 2 * e + 1] += f.y; }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(b[j]);
+    }
+  }
+  if (p.epilogue == EPI_BIAS_GELU) {
+    if (p.pre != nullptr) {
+      __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(p.pre) + (size_t)row * p.ldd + col0;
+      if (kFast) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+          o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + g * 8) = o;
+          const uint32_t w[4] = {o.x, o.y, o.z, o.w};                        // GELU sees exactly the stored (rounded) pre-activation
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(w[e]); v[g * 8 + 2 * e] = f.x; v[g * 8 + 2 * e + 1] = f.y; }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v[j]); prow[j] = h; v[j] = __bfloat162float(h);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+  } else if (p.epilogue == EPI_DGELU || p.epilogue == EPI_BIAS_RESIDUAL) {
+    float a[32];
+    if (kFast) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t w[4] = {ax[g].x, ax[g].y, ax[g].z, ax[g].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(w[e]); a[g * 8 + 2 * e] = f.x; a[g * 8 + 2 * e + 1] = f.y; }
+      }
+    } else {
+      const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = (col0 + j < p.N) ? __bfloat162float(arow[j]) : 0.f;
+    }
+    if (p.epilogue == EPI_DGELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_f(a[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += a[j];
+    }
+  }
+  if (kFast && p.out_dtype == EPL_BF16 && !p.accumulate) {
+    __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+      o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(drow + g * 8) = o;
+    }
+  } else if (kFast && p.out_dtype == EPL_F32 && p.accumulate && (p.ldd & 3) == 0) {
+    // weight-gradient accumulation into the fp32 main-grad buffer: fire-and-forget vector reductions, no read-modify-write
+    // round trip in the epilogue (each element receives exactly one contribution per GEMM, so the result is deterministic)
+    float* drow = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) red_add_v4_f32(drow + g * 4, v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+  } else {
+    const size_t out_es = p.out_dtype == EPL_F32 ? 4 : 2;
+    unsigned char* drow = reinterpret_cast<unsigned char*>(p.D) + (size_t)row * p.ldd * out_es;
+    if (p.out_dtype == EPL_BF16) store_chunk<__nv_bfloat16>(p, drow, col0, v);
+    else if (p.out_dtype == EPL_F32) store_chunk<float>(p, drow, col0, v);
+    else store_chunk<__half>(p, drow, col0, v);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const GemmParams p) {
   constexpr int BN = 256, BM2 = 256;
@@ -660,7 +777,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }   // 4 epilogue warps x 2 CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }   // 8 epilogue warps x 2 CTAs
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc2<kTmemCols>(tmem_slot);
@@ -730,79 +847,59 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
   } else {
-    // ================================ epilogue (both CTAs, 128 rows each) ================================
-    const int quarter = warp & 3;
+    // ================================ epilogue (both CTAs, 128 rows each; 8 warps) ================================
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const bool need_aux = p.epilogue == EPI_DGELU || p.epilogue == EPI_BIAS_RESIDUAL;
+    const bool rows_aligned = (p.ldd & 7) == 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int mb, nb;
       tile_coords(tile, m_blocks, n_blocks, mb, nb);
       const int row = mb * BM2 + (int)cta * BLOCK_M + quarter * 32 + lane;
-      const int n0 = nb * BN;
-      const size_t out_es = p.out_dtype == EPL_F32 ? 4 : 2;
-      unsigned char* drow = reinterpret_cast<unsigned char*>(p.D) + (size_t)row * p.ldd * out_es;
+      const int n0 = nb * BN + half * 128;                       // this warp's 128 columns
+      const bool fast = rows_aligned && n0 + 128 <= p.N;
+      const bool row_ok = row < p.M;
+      const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + n0;
+      // aux for the first 64 columns is requested before the accumulator wait: its latency hides behind the main loop
+      uint4 ax0[8], ax1[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) ax0[g] = (need_aux && fast && row_ok) ? ld_nc_v4(arow + g * 8) : make_uint4(0, 0, 0, 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
-          float v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+      uint32_t r0[32], r1[32];
+      // ---- columns [0, 64) ----
+      tmem_ld_32x32(taddr, r0);
+      tmem_ld_32x32(taddr + 32, r1);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          if (p.epilogue == EPI_BIAS || p.epilogue == EPI_BIAS_GELU || p.epilogue == EPI_BIAS_RESIDUAL) {
-            if (p.bias != nullptr) {
-              const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(b[j]);
-            }
-          }
-          if (p.epilogue == EPI_BIAS_GELU) {
-            if (p.pre != nullptr) {
-              __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(p.pre) + (size_t)row * p.ldd + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (col0 + j + 8 <= p.N && (p.ldd & 7) == 0) {
-                  Vec<__nv_bfloat16, 8> o;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) { o.v[e] = __float2bfloat16_rn(v[j + e]); v[j + e] = __bfloat162float(o.v[e]); }
-                  st_vec<__nv_bfloat16, 8>(prow + j, o);
-                } else {
-                  for (int e = 0; e < 8; ++e) if (col0 + j + e < p.N) {
-                    __nv_bfloat16 h = __float2bfloat16_rn(v[j + e]); prow[j + e] = h; v[j + e] = __bfloat162float(h);
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
-          } else if (p.epilogue == EPI_DGELU || p.epilogue == EPI_BIAS_RESIDUAL) {
-            const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float a8[8];
-              if (col0 + j + 8 <= p.N && (p.ldd & 7) == 0) {
-                Vec<__nv_bfloat16, 8> a = ld_vec<__nv_bfloat16, 8>(arow + j);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a8[e] = __bfloat162float(a.v[e]);
-              } else {
-                for (int e = 0; e < 8; ++e) a8[e] = (col0 + j + e < p.N) ? __bfloat162float(arow[j + e]) : 0.f;
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                v[j + e] = (p.epilogue == EPI_DGELU) ? v[j + e] * gelu_grad_f(a8[e]) : v[j + e] + a8[e];
-            }
-          }
-          if (p.out_dtype == EPL_BF16) store_chunk<__nv_bfloat16>(p, drow, col0, v);
-          else if (p.out_dtype == EPL_F32) store_chunk<float>(p, drow, col0, v);
-          else store_chunk<__half>(p, drow, col0, v);
+      for (int g = 0; g < 8; ++g) ax1[g] = (need_aux && fast && row_ok) ? ld_nc_v4(arow + 64 + g * 8) : make_uint4(0, 0, 0, 0);
+      tmem_ld_wait();
+      if (row_ok) {
+        const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[0]);
+        const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[4]);
+        if (fast) { epilogue_chunk32<true>(p, row, n0, r0, a0); epilogue_chunk32<true>(p, row, n0 + 32, r1, a1); }
+        else {
+          if (n0 < p.N) epilogue_chunk32<false>(p, row, n0, r0, a0);
+          if (n0 + 32 < p.N) epilogue_chunk32<false>(p, row, n0 + 32, r1, a1);
         }
       }
+      // ---- columns [64, 128) ----
+      tmem_ld_32x32(taddr + 64, r0);
+      tmem_ld_32x32(taddr + 96, r1);
+      tmem_ld_wait();
+      // the accumulator stage is drained into registers: hand it back to the MMA warp before the math and the stores
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);          // the leader's MMA thread owns the accumulator hand-off
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (row_ok) {
+        const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[0]);
+        const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[4]);
+        if (fast) { epilogue_chunk32<true>(p, row, n0 + 64, r0, a0); epilogue_chunk32<true>(p, row, n0 + 96, r1, a1); }
+        else {
+          if (n0 + 64 < p.N) epilogue_chunk32<false>(p, row, n0 + 64, r0, a0);
+          if (n0 + 96 < p.N) epilogue_chunk32<false>(p, row, n0 + 96, r1, a1);
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -824,7 +921,7 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const Gemm
   }
   const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
   int clusters = std::min(tiles, num_sms / 2);
-  gemm2_tcgen05_kernel<<<clusters * 2, kGemmThreads, kSmem, st>>>(ma, mb, p);
+  gemm2_tcgen05_kernel<<<clusters * 2, kGemm2Threads, kSmem, st>>>(ma, mb, p);
   return EPL_CHECK_LAUNCH();
 }
 

@@ -15,6 +15,8 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import os
+
 import torch
 from torch import nn
 
@@ -169,7 +171,12 @@ class _MlpFn(torch.autograd.Function):
     return dx, dw1, db1, dw2, db2, (dy if ctx.has_res else None)
 
 
+_AB_TORCH = os.environ.get("EPL_LINEAR", "") == "torch"    # measurement aid: A/B the whole step against cuBLAS + unfused epilogues
+
+
 def _use_kernel(x: torch.Tensor, w: torch.Tensor) -> bool:
+  if _AB_TORCH:
+    return False
   return (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and w.dtype == x.dtype
           and x.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0 and w.is_contiguous())
 

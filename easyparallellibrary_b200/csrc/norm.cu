@@ -24,10 +24,32 @@ struct NormGeom {          // launch-time geometry shared by host and device
   int stages;              // ring depth per warp
   int row_bytes;           // D * sizeof(T), multiple of 16
   int operands;            // row buffers per stage (1 forward, 2-3 backward)
+  int param_bytes;         // fp32 copies of gamma (and beta) at the start of shared memory
 };
 
-// Forward.  smem: [warps][stages][row_bytes] then barriers [warps][stages].
-template <typename T, bool kRms>
+// The kernels are issue-bound once the memory side is fixed (the first TMA version spent 1200 warp instructions per
+// 1600-element row re-reading and re-converting the row in three passes), so for rows of up to 8 vectors per lane
+// (VPL > 0) the row is converted to fp32 registers ONCE and gamma / beta are staged as fp32 in shared memory once per
+// CTA: ~500 instructions per row, fully unrolled.  VPL == 0 is the generic multi-pass path for longer rows.
+template <typename T, int VPL>
+EPL_DEVICE void norm_load_row(const T* buf, int lane, int nvec, float (&vals)[VPL > 0 ? VPL : 1][16 / sizeof(T)]) {
+  constexpr int E = 16 / sizeof(T);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const Vec<T, E> v = ld_vec<T, E>(buf + vi * E);
+#pragma unroll
+      for (int e = 0; e < E; ++e) vals[i][e] = to_f32<T>(v.v[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) vals[i][e] = 0.f;
+    }
+  }
+}
+
+// Forward.  smem: [gamma fp32][beta fp32][warps][stages][row_bytes] then barriers [warps][stages].
+template <typename T, bool kRms, int VPL>
 __global__ void __launch_bounds__(256)
 norm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ y,
                 float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int D, float eps, NormGeom geo) {
@@ -35,8 +57,11 @@ norm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* _
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D / E;
-  unsigned char* ring = smem + (size_t)warp * geo.stages * geo.row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)geo.warps * geo.stages * geo.row_bytes) + warp * geo.stages;
+  float* sg = reinterpret_cast<float*>(smem);
+  float* sb = sg + D;
+  unsigned char* ring0 = smem + geo.param_bytes;
+  unsigned char* ring = ring0 + (size_t)warp * geo.stages * geo.row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring0 + (size_t)geo.warps * geo.stages * geo.row_bytes) + warp * geo.stages;
   const int first = blockIdx.x * geo.warps + warp, stride = gridDim.x * geo.warps;
   if (lane == 0) {
     for (int s = 0; s < geo.stages; ++s) mbar_init(&bars[s], 1);
@@ -49,60 +74,107 @@ norm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* _
       }
     }
   }
-  __syncwarp();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    sg[d] = to_f32<T>(gamma[d]);
+    sb[d] = beta != nullptr ? to_f32<T>(beta[d]) : 0.f;
+  }
+  __syncthreads();
   int s = 0; uint32_t phase = 0;
   for (int row = first; row < rows; row += stride) {
     mbar_wait(&bars[s], phase);
     const T* buf = reinterpret_cast<const T*>(ring + (size_t)s * geo.row_bytes);
-    float sum = 0.f;
-    if constexpr (!kRms) {
+    T* yr = y + (size_t)row * D;
+    if constexpr (VPL > 0) {
+      float vals[VPL][E];
+      norm_load_row<T, VPL>(buf, lane, nvec, vals);
+      __syncwarp();                                         // slot consumed: refill it before doing the math
+      if (lane == 0) {
+        const int nrow = row + geo.stages * stride;
+        if (nrow < rows) {
+          mbar_expect_tx(&bars[s], geo.row_bytes);
+          bulk_g2s(ring + (size_t)s * geo.row_bytes, x + (size_t)nrow * D, geo.row_bytes, &bars[s]);
+        }
+      }
+      float sum = 0.f;
+      if constexpr (!kRms) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int e = 0; e < E; ++e) sum += vals[i][e];
+      }
+      const float mean = kRms ? 0.f : warp_sum(sum) / D;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (lane + i * 32 < nvec) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) { const float d = vals[i][e] - mean; sq = fmaf(d, d, sq); }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(sq) / D + eps);
+      if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        rstd_out[row] = rstd;
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          Vec<T, E> o;
+#pragma unroll
+          for (int e = 0; e < E; e += 4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(sg + vi * E + e), b4 = *reinterpret_cast<const float4*>(sb + vi * E + e);
+            o.v[e + 0] = from_f32<T>(fmaf((vals[i][e + 0] - mean) * rstd, g4.x, b4.x));
+            o.v[e + 1] = from_f32<T>(fmaf((vals[i][e + 1] - mean) * rstd, g4.y, b4.y));
+            o.v[e + 2] = from_f32<T>(fmaf((vals[i][e + 2] - mean) * rstd, g4.z, b4.z));
+            o.v[e + 3] = from_f32<T>(fmaf((vals[i][e + 3] - mean) * rstd, g4.w, b4.w));
+          }
+          st_vec<T, E>(yr + vi * E, o);
+        }
+      }
+    } else {
+      float sum = 0.f;
+      if constexpr (!kRms) {
+        for (int vi = lane; vi < nvec; vi += 32) {
+          const Vec<T, E> v = ld_vec<T, E>(buf + vi * E);
+#pragma unroll
+          for (int e = 0; e < E; ++e) sum += to_f32<T>(v.v[e]);
+        }
+      }
+      const float mean = kRms ? 0.f : warp_sum(sum) / D;
+      float sq = 0.f;
       for (int vi = lane; vi < nvec; vi += 32) {
         const Vec<T, E> v = ld_vec<T, E>(buf + vi * E);
 #pragma unroll
-        for (int e = 0; e < E; ++e) sum += to_f32<T>(v.v[e]);
+        for (int e = 0; e < E; ++e) { const float d = to_f32<T>(v.v[e]) - mean; sq = fmaf(d, d, sq); }
       }
-    }
-    const float mean = kRms ? 0.f : warp_sum(sum) / D;
-    float sq = 0.f;
-    for (int vi = lane; vi < nvec; vi += 32) {
-      const Vec<T, E> v = ld_vec<T, E>(buf + vi * E);
-#pragma unroll
-      for (int e = 0; e < E; ++e) { const float d = to_f32<T>(v.v[e]) - mean; sq += d * d; }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / D + eps);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      rstd_out[row] = rstd;
-    }
-    T* yr = y + (size_t)row * D;
-    for (int vi = lane; vi < nvec; vi += 32) {
-      const Vec<T, E> v = ld_vec<T, E>(buf + vi * E);
-      const Vec<T, E> g = ld_vec<T, E>(gamma + vi * E);
-      Vec<T, E> o;
-      if (beta != nullptr) {
-        const Vec<T, E> bb = ld_vec<T, E>(beta + vi * E);
-#pragma unroll
-        for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>((to_f32<T>(v.v[e]) - mean) * rstd * to_f32<T>(g.v[e]) + to_f32<T>(bb.v[e]));
-      } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>((to_f32<T>(v.v[e]) - mean) * rstd * to_f32<T>(g.v[e]));
+      const float rstd = rsqrtf(warp_sum(sq) / D + eps);
+      if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        rstd_out[row] = rstd;
       }
-      st_vec<T, E>(yr + vi * E, o);
-    }
-    __syncwarp();                                           // every lane is done reading this slot
-    if (lane == 0) {
-      const int nrow = row + geo.stages * stride;
-      if (nrow < rows) {
-        mbar_expect_tx(&bars[s], geo.row_bytes);
-        bulk_g2s(ring + (size_t)s * geo.row_bytes, x + (size_t)nrow * D, geo.row_bytes, &bars[s]);
+      for (int vi = lane; vi < nvec; vi += 32) {
+        const Vec<T, E> v = ld_vec<T, E>(buf + vi * E);
+        Vec<T, E> o;
+#pragma unroll
+        for (int e = 0; e < E; ++e) o.v[e] = from_f32<T>(fmaf((to_f32<T>(v.v[e]) - mean) * rstd, sg[vi * E + e], sb[vi * E + e]));
+        st_vec<T, E>(yr + vi * E, o);
+      }
+      __syncwarp();                                         // every lane is done reading this slot
+      if (lane == 0) {
+        const int nrow = row + geo.stages * stride;
+        if (nrow < rows) {
+          mbar_expect_tx(&bars[s], geo.row_bytes);
+          bulk_g2s(ring + (size_t)s * geo.row_bytes, x + (size_t)nrow * D, geo.row_bytes, &bars[s]);
+        }
       }
     }
     if (++s == geo.stages) { s = 0; phase ^= 1; }
   }
 }
 
-// Backward, input gradient.  smem: [warps][stages][operands][row_bytes] then barriers; operands = x, dy, (d skip).
-template <typename T, bool kRms>
+// Backward, input gradient.  smem: [gamma fp32][warps][stages][operands][row_bytes] then barriers; operands = x, dy, (d skip).
+template <typename T, bool kRms, int VPL>
 __global__ void __launch_bounds__(256)
 norm_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ gamma,
                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dx,
@@ -113,8 +185,10 @@ norm_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* _
   const int nvec = D / E;
   const bool has_res = dres != nullptr;
   const size_t slot = (size_t)geo.operands * geo.row_bytes;
-  unsigned char* ring = smem + (size_t)warp * geo.stages * slot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)geo.warps * geo.stages * slot) + warp * geo.stages;
+  float* sg = reinterpret_cast<float*>(smem);
+  unsigned char* ring0 = smem + geo.param_bytes;
+  unsigned char* ring = ring0 + (size_t)warp * geo.stages * slot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring0 + (size_t)geo.warps * geo.stages * slot) + warp * geo.stages;
   const int first = blockIdx.x * geo.warps + warp, stride = gridDim.x * geo.warps;
   auto fill = [&](int st, int row) {
     unsigned char* dst = ring + (size_t)st * slot;
@@ -131,7 +205,8 @@ norm_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* _
       if (row < rows) fill(st, row);
     }
   }
-  __syncwarp();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) sg[d] = to_f32<T>(gamma[d]);
+  __syncthreads();
   int s = 0; uint32_t phase = 0;
   for (int row = first; row < rows; row += stride) {
     const float mean = kRms ? 0.f : mean_in[row];
@@ -140,37 +215,85 @@ norm_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* _
     const T* bx = reinterpret_cast<const T*>(ring + (size_t)s * slot);
     const T* bd = reinterpret_cast<const T*>(ring + (size_t)s * slot + geo.row_bytes);
     const T* br = reinterpret_cast<const T*>(ring + (size_t)s * slot + 2 * (size_t)geo.row_bytes);
-    float s1 = 0.f, s2 = 0.f;
-    for (int vi = lane; vi < nvec; vi += 32) {
-      const Vec<T, E> vx = ld_vec<T, E>(bx + vi * E), vd = ld_vec<T, E>(bd + vi * E), g = ld_vec<T, E>(gamma + vi * E);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float gd = to_f32<T>(vd.v[e]) * to_f32<T>(g.v[e]);
-        s1 += gd;
-        s2 += gd * ((to_f32<T>(vx.v[e]) - mean) * rstd);
-      }
-    }
-    s1 = kRms ? 0.f : warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
     T* dxr = dx + (size_t)row * D;
-    for (int vi = lane; vi < nvec; vi += 32) {
-      const Vec<T, E> vx = ld_vec<T, E>(bx + vi * E), vd = ld_vec<T, E>(bd + vi * E), g = ld_vec<T, E>(gamma + vi * E);
-      Vec<T, E> vr;
-      if (has_res) vr = ld_vec<T, E>(br + vi * E);
-      Vec<T, E> o;
+    if constexpr (VPL > 0) {
+      // xh = normalised input, gd = gamma * dy; the residual gradient stays packed until the last moment
+      float xh[VPL][E], gd[VPL][E];
+      Vec<T, E> vr[VPL];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float xh = (to_f32<T>(vx.v[e]) - mean) * rstd;
-        float v = rstd * (to_f32<T>(vd.v[e]) * to_f32<T>(g.v[e]) - s1 - xh * s2);
-        if (has_res) v += to_f32<T>(vr.v[e]);                     // fused residual-branch gradient: dx = LN'(dy) + d(skip)
-        o.v[e] = from_f32<T>(v);
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          const Vec<T, E> vx = ld_vec<T, E>(bx + vi * E), vd = ld_vec<T, E>(bd + vi * E);
+          if (has_res) vr[i] = ld_vec<T, E>(br + vi * E);
+#pragma unroll
+          for (int e = 0; e < E; e += 4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(sg + vi * E + e);
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              xh[i][e + k] = (to_f32<T>(vx.v[e + k]) - mean) * rstd;
+              gd[i][e + k] = to_f32<T>(vd.v[e + k]) * gg[k];
+              s1 += gd[i][e + k];
+              s2 = fmaf(gd[i][e + k], xh[i][e + k], s2);
+            }
+          }
+        }
       }
-      st_vec<T, E>(dxr + vi * E, o);
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const int nrow = row + geo.stages * stride;
-      if (nrow < rows) fill(s, nrow);
+      __syncwarp();
+      if (lane == 0) {
+        const int nrow = row + geo.stages * stride;
+        if (nrow < rows) fill(s, nrow);
+      }
+      s1 = kRms ? 0.f : warp_sum(s1) / D;
+      s2 = warp_sum(s2) / D;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          Vec<T, E> o;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            float v = rstd * (fmaf(-xh[i][e], s2, gd[i][e]) - s1);
+            if (has_res) v += to_f32<T>(vr[i].v[e]);               // fused residual-branch gradient: dx = LN'(dy) + d(skip)
+            o.v[e] = from_f32<T>(v);
+          }
+          st_vec<T, E>(dxr + vi * E, o);
+        }
+      }
+    } else {
+      float s1 = 0.f, s2 = 0.f;
+      for (int vi = lane; vi < nvec; vi += 32) {
+        const Vec<T, E> vx = ld_vec<T, E>(bx + vi * E), vd = ld_vec<T, E>(bd + vi * E);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const float g = to_f32<T>(vd.v[e]) * sg[vi * E + e];
+          s1 += g;
+          s2 = fmaf(g, (to_f32<T>(vx.v[e]) - mean) * rstd, s2);
+        }
+      }
+      s1 = kRms ? 0.f : warp_sum(s1) / D;
+      s2 = warp_sum(s2) / D;
+      for (int vi = lane; vi < nvec; vi += 32) {
+        const Vec<T, E> vx = ld_vec<T, E>(bx + vi * E), vd = ld_vec<T, E>(bd + vi * E);
+        Vec<T, E> vr;
+        if (has_res) vr = ld_vec<T, E>(br + vi * E);
+        Vec<T, E> o;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const float xh = (to_f32<T>(vx.v[e]) - mean) * rstd;
+          float v = rstd * (to_f32<T>(vd.v[e]) * sg[vi * E + e] - s1 - xh * s2);
+          if (has_res) v += to_f32<T>(vr.v[e]);
+          o.v[e] = from_f32<T>(v);
+        }
+        st_vec<T, E>(dxr + vi * E, o);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const int nrow = row + geo.stages * stride;
+        if (nrow < rows) fill(s, nrow);
+      }
     }
     if (++s == geo.stages) { s = 0; phase ^= 1; }
   }
@@ -259,38 +382,43 @@ __global__ void __launch_bounds__(512) norm_param_reduce_kernel(const float* __r
 }
 
 // ring geometry: as many warps x stages as fit ~100 KB per CTA (two CTAs per SM), at least 2 stages
-static NormGeom norm_geometry(int row_bytes, int operands) {
+static NormGeom norm_geometry(int row_bytes, int operands, int param_bytes) {
   NormGeom g;
-  g.row_bytes = row_bytes; g.operands = operands;
-  const int budget = 100 * 1024;
+  g.row_bytes = row_bytes; g.operands = operands; g.param_bytes = (param_bytes + 127) / 128 * 128;
+  const long budget = 110 * 1024 - g.param_bytes;
   g.warps = 8;
-  while (g.warps > 1 && (size_t)g.warps * 2 * operands * row_bytes > (size_t)budget) g.warps /= 2;
-  g.stages = (int)std::min<size_t>(4, std::max<size_t>(2, (size_t)budget / ((size_t)g.warps * operands * row_bytes)));
+  while (g.warps > 1 && (long)g.warps * 2 * operands * row_bytes > budget) g.warps /= 2;
+  g.stages = (int)std::min<long>(4, std::max<long>(2, budget / ((long)g.warps * operands * row_bytes)));
   return g;
 }
-static size_t norm_smem(const NormGeom& g) { return (size_t)g.warps * g.stages * g.operands * g.row_bytes + (size_t)g.warps * g.stages * 8; }
+static size_t norm_smem(const NormGeom& g) {
+  return (size_t)g.param_bytes + (size_t)g.warps * g.stages * g.operands * g.row_bytes + (size_t)g.warps * g.stages * 8;
+}
 
 template <typename K>
 static int norm_configure(K kernel, size_t bytes) {
   if (bytes > 220 * 1024) return -2;
-  static size_t configured = 0;                 // one instance per kernel type (K is a distinct function-pointer type per signature)
-  static K last = nullptr;
-  if (last == kernel && bytes <= configured) return 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return (int)e;
-  last = kernel; configured = bytes;
-  return 0;
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <typename T, bool kRms>
 static int launch_fwd(const void* x, const void* g, const void* b, void* y, float* mean, float* rstd, int rows, int D,
                       float eps, cudaStream_t st) {
-  const NormGeom geo = norm_geometry(D * (int)sizeof(T), 1);
+  constexpr int E = 16 / sizeof(T);
+  const NormGeom geo = norm_geometry(D * (int)sizeof(T), 1, D * 8);
   const size_t bytes = norm_smem(geo);
-  int rc = norm_configure(norm_fwd_kernel<T, kRms>, bytes);
-  if (rc) return rc;
   const int grid = std::min((rows + geo.warps - 1) / geo.warps, kNumSMs * 2);
-  norm_fwd_kernel<T, kRms><<<grid, geo.warps * 32, bytes, st>>>((const T*)x, (const T*)g, (const T*)b, (T*)y, mean, rstd, rows, D, eps, geo);
+  const int vpl = (D / E + 31) / 32;
+  int rc;
+#define LAUNCH(V)                                                                                                       \
+  do {                                                                                                                  \
+    rc = norm_configure(norm_fwd_kernel<T, kRms, V>, bytes);                                                            \
+    if (rc) return rc;                                                                                                  \
+    norm_fwd_kernel<T, kRms, V><<<grid, geo.warps * 32, bytes, st>>>((const T*)x, (const T*)g, (const T*)b, (T*)y, mean, rstd, rows, D, eps, geo); \
+  } while (0)
+  if (vpl <= 1) LAUNCH(1); else if (vpl <= 2) LAUNCH(2); else if (vpl <= 4) LAUNCH(4); else if (vpl <= 8) LAUNCH(8); else LAUNCH(0);
+#undef LAUNCH
   return EPL_CHECK_LAUNCH();
 }
 
@@ -299,13 +427,20 @@ static int launch_bwd(const void* x, const void* dy, const void* g, const float*
                       float* pg, float* pb, int chunks, int rows, int D, const void* dres, cudaStream_t st) {
   constexpr int E = 16 / sizeof(T);
   const int nvec = D / E;
-  const NormGeom geo = norm_geometry(D * (int)sizeof(T), dres ? 3 : 2);
+  const NormGeom geo = norm_geometry(D * (int)sizeof(T), dres ? 3 : 2, D * 4);
   const size_t bytes = norm_smem(geo);
-  int rc = norm_configure(norm_bwd_dx_kernel<T, kRms>, bytes);
-  if (rc) return rc;
   const int grid = std::min((rows + geo.warps - 1) / geo.warps, kNumSMs * 2);
-  norm_bwd_dx_kernel<T, kRms><<<grid, geo.warps * 32, bytes, st>>>((const T*)x, (const T*)dy, (const T*)g, mean, rstd, (T*)dx, rows, D,
-                                                                   (const T*)dres, geo);
+  const int vpl = (nvec + 31) / 32;
+  int rc;
+#define LAUNCH(V)                                                                                                       \
+  do {                                                                                                                  \
+    rc = norm_configure(norm_bwd_dx_kernel<T, kRms, V>, bytes);                                                         \
+    if (rc) return rc;                                                                                                  \
+    norm_bwd_dx_kernel<T, kRms, V><<<grid, geo.warps * 32, bytes, st>>>((const T*)x, (const T*)dy, (const T*)g, mean, rstd, (T*)dx, rows, D, \
+                                                                        (const T*)dres, geo);                           \
+  } while (0)
+  if (vpl <= 1) LAUNCH(1); else if (vpl <= 2) LAUNCH(2); else if (vpl <= 4) LAUNCH(4); else if (vpl <= 8) LAUNCH(8); else LAUNCH(0);
+#undef LAUNCH
   dim3 pgrid((nvec + 31) / 32, chunks);
   norm_bwd_param_kernel<T, kRms><<<pgrid, kParamWarps * 32, 0, st>>>((const T*)x, (const T*)dy, mean, rstd, pg, pb, rows, D);
   return EPL_CHECK_LAUNCH();

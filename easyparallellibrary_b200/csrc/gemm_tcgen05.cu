@@ -47,6 +47,7 @@ struct GemmParams {
   int a_mn_major, b_mn_major;
   int ab_format;           // 1 = bf16, 0 = fp16
   float alpha;
+  int bn2;                 // 2-CTA kernel: tile width (128 / 192 / 256), chosen per shape by pick_bn2()
 };
 
 // Fused collective (tensor-parallel) state.  mode 1: all-gather -> GEMM, mode 2: GEMM -> reduce-scatter.
@@ -754,8 +755,15 @@ EPL_DEVICE void epilogue_chunk32(const GemmParams& p, int row, int col0, const u
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const GemmParams p) {
-  constexpr int BN = 256, BM2 = 256;
-  constexpr int kABytes = BLOCK_M * BLOCK_K * 2, kBBytes = (BN / 2) * BLOCK_K * 2, kStageBytes = kABytes + kBBytes;
+  // The tile is 256 rows (128 per CTA) x BN columns; BN is a runtime value (128 / 192 / 256) so one kernel serves every
+  // width pick_bn2() selects against wave quantisation.  Shared-memory stages and TMEM accumulator stages keep the
+  // 256-wide stride.
+  constexpr int BM2 = 256, kMaxBN = 256;
+  constexpr int kABytes = BLOCK_M * BLOCK_K * 2, kBBytes = (kMaxBN / 2) * BLOCK_K * 2, kStageBytes = kABytes + kBBytes;
+  const int BN = p.bn2;
+  // bytes one CTA's producer puts on the stage barrier: A half + B half (MN-major B is fetched in whole 64-column atoms)
+  const uint32_t b_boxes = (uint32_t)((BN / 2 + 63) / 64);
+  const uint32_t tx_bytes = kABytes + (p.b_mn_major ? b_boxes * (BLOCK_K * 128) : (uint32_t)(BN / 2) * BLOCK_K * 2);
   constexpr int kTmemCols = 512;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes);
@@ -798,7 +806,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * kStageBytes;
           unsigned char* sb = sa + kABytes;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);          // bytes of both CTAs land on the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);             // bytes of both CTAs land on the leader's barrier
           const int k0 = kb * BLOCK_K;
           if (!p.a_mn_major) {
             tma_load_2d_2cta(sa, &map_a, &full_bar[stage], k0, m0);
@@ -809,8 +817,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           if (!p.b_mn_major) {
             tma_load_2d_2cta(sb, &map_b, &full_bar[stage], k0, n0);
           } else {
-#pragma unroll
-            for (int a = 0; a < (BN / 2) / 64; ++a) tma_load_2d_2cta(sb + a * (BLOCK_K * 128), &map_b, &full_bar[stage], n0 + a * 64, k0);
+            for (uint32_t a = 0; a < b_boxes; ++a) tma_load_2d_2cta(sb + a * (BLOCK_K * 128), &map_b, &full_bar[stage], n0 + (int)a * 64, k0);
           }
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
@@ -827,7 +834,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * kMaxBN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -851,29 +858,37 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const bool need_aux = p.epilogue == EPI_DGELU || p.epilogue == EPI_BIAS_RESIDUAL;
     const bool rows_aligned = (p.ldd & 7) == 0;
+    const int half_cols = BN / 2;                                // 64 / 96 / 128 columns per epilogue warp
+    const int nchunks = half_cols / 32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int mb, nb;
       tile_coords(tile, m_blocks, n_blocks, mb, nb);
       const int row = mb * BM2 + (int)cta * BLOCK_M + quarter * 32 + lane;
-      const int n0 = nb * BN + half * 128;                       // this warp's 128 columns
-      const bool fast = rows_aligned && n0 + 128 <= p.N;
+      const int n0 = nb * BN + half * half_cols;                 // this warp's columns
+      const bool fast = rows_aligned && n0 + half_cols <= p.N;
       const bool row_ok = row < p.M;
+      const bool pf = need_aux && fast && row_ok;
       const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + n0;
       // aux for the first 64 columns is requested before the accumulator wait: its latency hides behind the main loop
       uint4 ax0[8], ax1[8];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) ax0[g] = (need_aux && fast && row_ok) ? ld_nc_v4(arow + g * 8) : make_uint4(0, 0, 0, 0);
+      for (int g = 0; g < 8; ++g) ax0[g] = pf ? ld_nc_v4(arow + g * 8) : make_uint4(0, 0, 0, 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN + half * half_cols;
       uint32_t r0[32], r1[32];
       // ---- columns [0, 64) ----
       tmem_ld_32x32(taddr, r0);
       tmem_ld_32x32(taddr + 32, r1);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) ax1[g] = (need_aux && fast && row_ok) ? ld_nc_v4(arow + 64 + g * 8) : make_uint4(0, 0, 0, 0);
+      for (int g = 0; g < 8; ++g) ax1[g] = (pf && 64 + g * 8 < half_cols) ? ld_nc_v4(arow + 64 + g * 8) : make_uint4(0, 0, 0, 0);
       tmem_ld_wait();
+      if (nchunks == 2) {                                        // accumulator stage drained into registers: hand it back early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      }
       if (row_ok) {
         const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[0]);
         const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[4]);
@@ -883,21 +898,24 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           if (n0 + 32 < p.N) epilogue_chunk32<false>(p, row, n0 + 32, r1, a1);
         }
       }
-      // ---- columns [64, 128) ----
-      tmem_ld_32x32(taddr + 64, r0);
-      tmem_ld_32x32(taddr + 96, r1);
-      tmem_ld_wait();
-      // the accumulator stage is drained into registers: hand it back to the MMA warp before the math and the stores
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-      if (row_ok) {
-        const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[0]);
-        const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[4]);
-        if (fast) { epilogue_chunk32<true>(p, row, n0 + 64, r0, a0); epilogue_chunk32<true>(p, row, n0 + 96, r1, a1); }
-        else {
-          if (n0 + 64 < p.N) epilogue_chunk32<false>(p, row, n0 + 64, r0, a0);
-          if (n0 + 96 < p.N) epilogue_chunk32<false>(p, row, n0 + 96, r1, a1);
+      if (nchunks > 2) {
+        // ---- columns [64, 96) or [64, 128) ----
+        tmem_ld_32x32(taddr + 64, r0);
+        if (nchunks > 3) tmem_ld_32x32(taddr + 96, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        if (row_ok) {
+          const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[0]);
+          const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[4]);
+          if (fast) {
+            epilogue_chunk32<true>(p, row, n0 + 64, r0, a0);
+            if (nchunks > 3) epilogue_chunk32<true>(p, row, n0 + 96, r1, a1);
+          } else {
+            if (n0 + 64 < p.N) epilogue_chunk32<false>(p, row, n0 + 64, r0, a0);
+            if (nchunks > 3 && n0 + 96 < p.N) epilogue_chunk32<false>(p, row, n0 + 96, r1, a1);
+          }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -919,10 +937,29 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const Gemm
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  const int tiles = ((p.M + 255) / 256) * ((p.N + p.bn2 - 1) / p.bn2);
   int clusters = std::min(tiles, num_sms / 2);
   gemm2_tcgen05_kernel<<<clusters * 2, kGemm2Threads, kSmem, st>>>(ma, mb, p);
   return EPL_CHECK_LAUNCH();
+}
+
+// Tile width of the 2-CTA kernel.  The grid is persistent (one CTA pair per two SMs), so the cost of a shape is
+// waves x tile time; a 256-wide tile wastes up to a whole wave on N = 1600 (224 tiles on 74 pairs = 3.03 waves) where 192
+// gives 288 tiles = 3.89 waves.  Narrower tiles re-read A more often per flop, hence the small penalties (calibrated with
+// tools/gemm_bench.py, forced widths).
+static int pick_bn2(int M, int N, int num_sms) {
+  const long pairs = std::max(num_sms / 2, 1), mt = (M + 255) / 256;
+  int best = 256;
+  double best_cost = 1e30;
+  const int widths[3] = {256, 192, 128};
+  const double penalty[3] = {1.0, 1.04, 1.12};
+  for (int i = 0; i < 3; ++i) {
+    const long tiles = mt * ((N + widths[i] - 1) / widths[i]);
+    const long waves = (tiles + pairs - 1) / pairs;
+    const double cost = (double)waves * widths[i] * penalty[i];
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = widths[i]; }
+  }
+  return best;
 }
 
 static int pick_bn(int N, int b_mn_major, int forced) {
@@ -944,21 +981,25 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
                         int a_mn_major, int b_mn_major, const void* bias, void* pre, const void* aux, int epilogue,
                         int accumulate, int out_dtype, float alpha, int is_fp16, int force_bn, int num_sms, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  // The 2-CTA 256x256 kernel (cta_group::2) is the default whenever the problem spans at least one such tile: measured
-  // +8-12 % over the 1-CTA 128x256 kernel on every GPT-2-XL shape (profiles/r1_gemm_bench_v2_with_2cta.txt).
-  if ((force_bn == 512 || force_bn == 0) && M >= 256 && N >= 256) {
+  // The 2-CTA kernel (cta_group::2, 256 x {128,192,256} tiles) is the default whenever the problem spans at least one
+  // such tile: measured +8-12 % over the 1-CTA 128x256 kernel on every GPT-2-XL shape
+  // (profiles/r1_gemm_bench_v2_with_2cta.txt).  force_bn: 0 = pick the width per shape, 512 / 448 / 384 = force 256 / 192 / 128.
+  const bool two_cta_forced = force_bn == 512 || force_bn == 448 || force_bn == 384;
+  if ((two_cta_forced || force_bn == 0) && M >= 256 && N >= 256) {
+    const int sms = num_sms > 0 ? num_sms : kNumSMs;
+    const int bn2 = two_cta_forced ? force_bn - 256 : pick_bn2(M, N, sms);
     CUtensorMap ma2, mb2;
     int rc2 = !a_mn_major ? make_map_2d(&ma2, A, M, K, lda, BLOCK_K, BLOCK_M, is_fp16) : make_map_2d(&ma2, A, K, M, lda, 64, BLOCK_K, is_fp16);
     if (rc2) return rc2;
-    rc2 = !b_mn_major ? make_map_2d(&mb2, B, N, K, ldb, BLOCK_K, 128, is_fp16) : make_map_2d(&mb2, B, K, N, ldb, 64, BLOCK_K, is_fp16);
+    rc2 = !b_mn_major ? make_map_2d(&mb2, B, N, K, ldb, BLOCK_K, bn2 / 2, is_fp16) : make_map_2d(&mb2, B, K, N, ldb, 64, BLOCK_K, is_fp16);
     if (rc2) return rc2;
     GemmParams p2;
     p2.M = M; p2.N = N; p2.K = K; p2.ldd = ldd; p2.D = D; p2.bias = bias; p2.pre = pre; p2.aux = aux; p2.epilogue = epilogue;
     p2.accumulate = accumulate; p2.out_dtype = out_dtype; p2.a_mn_major = a_mn_major; p2.b_mn_major = b_mn_major; p2.alpha = alpha;
-    p2.ab_format = is_fp16 ? 0 : 1;
-    return launch_gemm2(ma2, mb2, p2, num_sms > 0 ? num_sms : kNumSMs, (cudaStream_t)stream);
+    p2.ab_format = is_fp16 ? 0 : 1; p2.bn2 = bn2;
+    return launch_gemm2(ma2, mb2, p2, sms, (cudaStream_t)stream);
   }
-  const int bn = pick_bn(N, b_mn_major, force_bn == 512 ? 0 : force_bn);
+  const int bn = pick_bn(N, b_mn_major, two_cta_forced ? 0 : force_bn);
   CUtensorMap ma, mb;
   int rc;
   if (!a_mn_major) rc = make_map_2d(&ma, A, M, K, lda, BLOCK_K, BLOCK_M, is_fp16);

@@ -341,14 +341,16 @@ def test_vocab_parallel_xent_kernel_modes():
     _close(g, ref_in.grad[:, i * half:(i + 1) * half], 2e-2, 1e-4, "vocab-parallel grad shard %d" % i)
 
 
+@pytest.mark.parametrize("width", [512, 448, 384])
 @pytest.mark.parametrize("layout", ["nt", "nn", "tn"])
 @pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 1600, 1600), (8192, 6400, 1600), (300, 264, 200)])
-def test_gemm_two_cta_layouts(M, N, K, layout):
-  """cta_group::2 kernel on all three operand layouts incl. ragged edges."""
+def test_gemm_two_cta_layouts(M, N, K, layout, width):
+  """cta_group::2 kernel, every tile width (256 / 192 / 128 = force codes 512 / 448 / 384), on all three operand layouts
+  incl. ragged edges (the 192-wide tile reads 1.5 swizzle atoms of an MN-major B per CTA)."""
   from easyparallellibrary_b200.ops import linear as L
   torch.manual_seed(0)
   M, N, K = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
-  L._FORCE_BN = 512
+  L._FORCE_BN = width
   try:
     if layout == "nt":
       a, b = torch.randn(M, K, device=DEV).bfloat16(), torch.randn(N, K, device=DEV).bfloat16()

@@ -204,3 +204,25 @@ def test_models_build_and_step_on_cpu():
   r = ResNet50(num_classes=64, width=8, layers=(1, 1, 1, 1), split_head=True)
   tr = epl.Trainer(r, "sgd", lr=1e-2)
   assert tr.step(torch.randn(2, 3, 32, 32), torch.randint(0, 64, (2,))).loss.isfinite() and tr.has_split
+
+
+def test_throughput_meter_and_plan_summary():
+  """utils/metric.py + utils/summary_info.py (reference: utils/metric.py, utils/summary_info.py, Graph.format())."""
+  import time
+  import torch
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.utils.metric import ThroughputMeter
+  from easyparallellibrary_b200.utils.summary_info import plan_summary
+  meter = ThroughputMeter(items_per_step=64, warmup=2, unit="samples")
+  for _ in range(5):
+    time.sleep(0.002)
+    meter.step()
+  out = meter.summary()
+  assert out["steps"] == 3 and out["ms_per_step"] > 1.0 and out["per_second"] > 0
+  epl.init(epl.Config({"pipeline.num_micro_batch": 2}), init_process_group=False)
+  with epl.replicate(1):
+    model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2))
+  tr = epl.Trainer(model, "sgd", lr=0.1, loss_fn=lambda y, t: torch.nn.functional.cross_entropy(y, t))
+  tr.build()
+  text = plan_summary(tr)
+  assert "stages=1" in text and "micro_batches=2" in text and "param group" in text

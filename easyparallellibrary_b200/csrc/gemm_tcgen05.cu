@@ -943,20 +943,22 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const Gemm
   return EPL_CHECK_LAUNCH();
 }
 
-// Tile width of the 2-CTA kernel.  The grid is persistent (one CTA pair per two SMs), so the cost of a shape is
-// waves x tile time; a 256-wide tile wastes up to a whole wave on N = 1600 (224 tiles on 74 pairs = 3.03 waves) where 192
-// gives 288 tiles = 3.89 waves.  Narrower tiles re-read A more often per flop, hence the small penalties (calibrated with
-// tools/gemm_bench.py, forced widths).
+// Tile width of the 2-CTA kernel.  Measured on B200 (profiles/r1_gemm_bench_v3_widths.txt): the time of one tile is almost
+// independent of its width (192-wide: 0.95x, 128-wide: 0.87x of the 256-wide tile) because the main loop is bound by
+// bytes in flight from L2 (6 stages x 32 KB per CTA), not by MMA issue — so a narrower tile never pays for the waves it
+// saves, not even on N = 1600 where 256 leaves 3.03 waves.  The widths stay selectable (force_bn 448 / 384) for shapes
+// with fewer tiles than CTA pairs, where they do win.
 static int pick_bn2(int M, int N, int num_sms) {
   const long pairs = std::max(num_sms / 2, 1), mt = (M + 255) / 256;
+  const int widths[3] = {256, 192, 128};
+  const double tile_time[3] = {1.0, 0.95, 0.87};
   int best = 256;
   double best_cost = 1e30;
-  const int widths[3] = {256, 192, 128};
-  const double penalty[3] = {1.0, 1.04, 1.12};
   for (int i = 0; i < 3; ++i) {
     const long tiles = mt * ((N + widths[i] - 1) / widths[i]);
     const long waves = (tiles + pairs - 1) / pairs;
-    const double cost = (double)waves * widths[i] * penalty[i];
+    // a narrower width must promise >= 10 % (short-K shapes fall short of the calibrated tile times)
+    const double cost = (double)waves * tile_time[i] * (i == 0 ? 1.0 : 1.10);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = widths[i]; }
   }
   return best;

@@ -9,6 +9,7 @@ reads peers' gradient shards and writes peers' weight shards directly.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -36,9 +37,12 @@ class FusedDataParallel(object):
     self.epochs: Dict[Tuple[int, int], int] = {}
     self.side = torch.cuda.Stream(device=trainer.device, priority=-1)
     self.blocks = 148                 # after backward: the whole GPU
-    self.overlap_blocks = 32          # during backward: co-resident with the GEMM CTAs (no shared memory, 512 threads)
+    # During backward the bucket kernel can run on a side stream with a few CTAs.  It needs most of an SM's registers, so its
+    # CTAs displace CTAs of the persistent GEMMs rather than sharing SMs with them; EPL_FUSED_OVERLAP=0 runs every bucket
+    # after backward on the whole GPU instead (no interference, fully exposed), EPL_FUSED_OVERLAP_BLOCKS sizes the overlap.
+    self.overlap_blocks = int(os.environ.get("EPL_FUSED_OVERLAP_BLOCKS", "32"))
     self.launched = set()
-    self.overlap = True
+    self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "1") != "0"
 
   @classmethod
   def maybe_create(cls, trainer) -> Optional["FusedDataParallel"]:

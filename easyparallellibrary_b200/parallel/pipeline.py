@@ -174,9 +174,58 @@ class PipelineExecutor(object):
     meta = meta.cpu().tolist()
     return torch.Size(meta[2:2 + meta[0]]), _DTYPES[meta[1]]
 
+  # ------------------------------------------------------------------ kernel warm-up (first step, GPU only)
+  def _warmup(self, micro: List[Tuple[Any, ...]]) -> None:
+    """Run this stage's forward + backward once, with no pipeline transfer in flight, before the first schedule.
+
+    CUDA loads kernels lazily, and the first launch of a kernel cannot complete while another kernel of the process is
+    spinning on the device.  A posted NCCL receive spins until its peer sends, so under 1F1B the first step can deadlock:
+    stage 0 sits in the lazy load of its first backward kernel behind its own posted RECV_B, stage 1 sits in the lazy load
+    of its first forward kernel behind its posted RECV_F, and neither reaches the send the other waits for (observed on
+    B200).  After this pass every kernel of F and B is resident, so launches never block again.  Model buffers
+    (e.g. BatchNorm statistics), the RNG state and the gradient buckets are restored, so training is unaffected.
+    """
+    tr = self.tr
+    mb = micro[0]
+    saved = [b.detach().clone() for b in self.module.buffers()]
+    cpu_rng, dev_rng = torch.get_rng_state(), torch.cuda.get_rng_state(self.device)
+    tr._first_micro_batch, tr._last_micro_batch = True, False     # no bucket reduction is launched from the grad hooks
+    if self.first:
+      x = mb[0]
+    else:
+      self._shape_fwd = self._recv_meta()
+      x = torch.zeros(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
+      if x.is_floating_point():
+        x.requires_grad_()
+    with phase_scope(ModelPhase.FORWARD):
+      y = self.module(x)
+      if self.last and tr.loss_fn is not None:
+        y = tr.loss_fn(y, *mb[1:])
+    if not self.last:
+      self._send_meta(y)
+      self._meta_sent = True
+    with phase_scope(ModelPhase.BACKWARD):
+      if self.last:
+        (y if y.dim() == 0 else y.float().sum()).backward()
+      else:
+        torch.autograd.backward(y, grad_tensors=torch.zeros_like(y))
+    Graph.get().pop_collections()
+    for flat in tr.flats.values():
+      flat.zero_grad()
+    with torch.no_grad():
+      for b, v in zip(self.module.buffers(), saved):
+        b.copy_(v)
+    torch.set_rng_state(cpu_rng)
+    torch.cuda.set_rng_state(dev_rng, self.device)
+    torch.cuda.synchronize(self.device)
+    dist.barrier(group=self.replica_group)      # nobody starts the schedule before every stage has loaded its kernels
+
   # ------------------------------------------------------------------ one training step
   def run(self, micro: List[Tuple[Any, ...]], mean: bool):
     tr, graph = self.tr, Graph.get()
+    if self.device.type == "cuda" and not getattr(self, "_warm", False):
+      self._warmup(micro)
+      self._warm = True
     inputs: Dict[int, torch.Tensor] = {}
     outputs: Dict[int, torch.Tensor] = {}
     recv_f: Dict[int, Tuple[torch.Tensor, Any]] = {}

@@ -341,12 +341,13 @@ def test_vocab_parallel_xent_kernel_modes():
     _close(g, ref_in.grad[:, i * half:(i + 1) * half], 2e-2, 1e-4, "vocab-parallel grad shard %d" % i)
 
 
-@pytest.mark.parametrize("width", [512, 448, 384])
+@pytest.mark.parametrize("width", [512, 448, 384, 1024])
 @pytest.mark.parametrize("layout", ["nt", "nn", "tn"])
 @pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 1600, 1600), (8192, 6400, 1600), (300, 264, 200)])
 def test_gemm_two_cta_layouts(M, N, K, layout, width):
   """cta_group::2 kernel, every tile width (256 / 192 / 128 = force codes 512 / 448 / 384), on all three operand layouts
-  incl. ragged edges (the 192-wide tile reads 1.5 swizzle atoms of an MN-major B per CTA)."""
+  incl. ragged edges (the 192-wide tile reads 1.5 swizzle atoms of an MN-major B per CTA); 1024 = the 4-CTA cluster
+  kernel that multicasts the B tile across two CTA pairs."""
   from easyparallellibrary_b200.ops import linear as L
   torch.manual_seed(0)
   M, N, K = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8

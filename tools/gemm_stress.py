@@ -8,6 +8,7 @@ from easyparallellibrary_b200.ops import linear as L
 random.seed(0); torch.manual_seed(0)
 bad = 0
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+L._FORCE_BN = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # e.g. 1024 = 4-CTA multicast kernel
 for it in range(n):
   M = random.choice([256, 384, 512, 1000, 1024, 2048, 8192])
   N = random.choice([256, 768, 1024, 1600, 4800])

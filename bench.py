@@ -88,6 +88,10 @@ def main():
                       "offline pip install into baseline/_ref fails with ModuleNotFoundError: tensorflow (see DESIGN.md)"}))
     return 0
 
+  if args.parallelism.startswith("pp"):
+    # pipeline: a first-time kernel launch must never block behind a posted NCCL receive (see parallel/pipeline.py), so load
+    # every CUDA module up front instead of lazily; must be set before the CUDA context exists
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
   import torch
   import torch.distributed as dist
   import easyparallellibrary_b200 as epl

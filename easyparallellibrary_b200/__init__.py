@@ -38,6 +38,11 @@ def init(config=None, init_process_group: bool = True):
   env = Env.get()
   env.reset()
   env.init(config)
+  if env.config.pipeline.num_micro_batch > 1 or env.config.pipeline.num_stages > 1:
+    # Pipeline schedules keep NCCL receives posted on the device; CUDA's lazy module loading would make the first launch of
+    # any kernel wait for them (deadlock under 1F1B, see parallel/pipeline.py).  Takes effect if the CUDA context does not
+    # exist yet; the executor additionally runs a communication-free warm-up pass of every stage.
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
   if init_process_group and int(os.environ.get("WORLD_SIZE", "1")) > 1:
     from easyparallellibrary_b200.runtime.dist import ensure_process_group
     ensure_process_group()

@@ -42,7 +42,7 @@ class FusedDataParallel(object):
     # after backward on the whole GPU instead (no interference, fully exposed), EPL_FUSED_OVERLAP_BLOCKS sizes the overlap.
     self.overlap_blocks = int(os.environ.get("EPL_FUSED_OVERLAP_BLOCKS", "32"))
     self.launched = set()
-    self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "1") != "0"
+    self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "0") != "0"   # measured on 2 x B200: 117.7 ms/step off vs 122.8 ms on (GPT-2-XL)
 
   @classmethod
   def maybe_create(cls, trainer) -> Optional["FusedDataParallel"]:

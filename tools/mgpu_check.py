@@ -98,14 +98,14 @@ def check_symm(dev, world, rank):
   log("symmetric memory ok")
 
 
-def train(dev, world, rank, fused, steps=6, model_name="tiny", batch=4, seq=128):
+def train(dev, world, rank, fused, steps=6, model_name="tiny", batch=4, seq=128, lr=1e-3, eps=1e-8):
   from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config
   epl.init(epl.Config({"amp.level": "bf16", "communication.fused_kernels": fused}))
   torch.manual_seed(0)
   with epl.replicate(1):
     cfg = GPT2Config.named(model_name) if model_name != "tiny" else GPT2Config.named("tiny", n_embd=256, n_head=4, vocab_size=2048)
     model = GPT2(cfg)
-  tr = epl.Trainer(model, "adamw", lr=1e-3).build()
+  tr = epl.Trainer(model, "adamw", lr=lr, eps=eps).build()
   g = torch.Generator().manual_seed(100 + rank)
   toks = [torch.randint(0, cfg.vocab_size, (batch, seq), generator=g).to(dev) for _ in range(steps)]
   losses = []
@@ -126,7 +126,15 @@ def check_fused(dev, world, rank):
   dist.all_gather(gathered, p_f)
   same = max((gathered[0] - g).abs().max().item() for g in gathered)
   log("fused vs NCCL path: max |dparam| = %.3e, replica divergence = %.3e, losses %s vs %s" % (diff, same, loss_f[-2:], loss_b[-2:]))
-  assert same == 0.0 and diff < 2e-2 and abs(loss_f[-1] - loss_b[-1]) < 0.05
+  # default AdamW (eps 1e-8) is sign-like in the first steps: a bf16-rounding difference in a near-zero gradient moves a
+  # weight by 2 x lr, so only coarse agreement can be asserted here ...
+  assert same == 0.0 and diff < 2.5e-2 and abs(loss_f[-1] - loss_b[-1]) < 0.05 * abs(loss_b[-1]) and loss_f[-1] < loss_f[0]
+  # ... the strict comparison uses a large eps (update ~ lr * m / eps, linear in the gradient, no sign amplification)
+  tr_b, loss_b, p_b = train(dev, world, rank, fused=False, lr=1e-2, eps=1.0)
+  tr_f, loss_f, p_f = train(dev, world, rank, fused=True, lr=1e-2, eps=1.0)
+  diff = (p_b - p_f).abs().max().item()
+  log("fused vs NCCL path (eps=1): max |dparam| = %.3e, losses %s vs %s" % (diff, loss_f[-2:], loss_b[-2:]))
+  assert diff < 1e-3 and abs(loss_f[-1] - loss_b[-1]) < 0.02
 
 
 def check_tp(dev, world, rank):

@@ -134,7 +134,8 @@ def check_fused(dev, world, rank):
   tr_f, loss_f, p_f = train(dev, world, rank, fused=True, lr=1e-2, eps=1.0)
   diff = (p_b - p_f).abs().max().item()
   log("fused vs NCCL path (eps=1): max |dparam| = %.3e, losses %s vs %s" % (diff, loss_f[-2:], loss_b[-2:]))
-  assert diff < 1e-3 and abs(loss_f[-1] - loss_b[-1]) < 0.02
+  # parameters are compared in bf16: one ulp is 3.9e-3 for the LayerNorm gains near 1
+  assert diff < 8e-3 and abs(loss_f[-1] - loss_b[-1]) < 0.01
 
 
 def check_tp(dev, world, rank):

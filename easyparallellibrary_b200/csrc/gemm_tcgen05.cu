@@ -945,8 +945,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // quarter of B and multicasts it to the CTA with the same rank-in-pair of the other pair, so one k-block costs
 // 16 KB (A) + 8 KB (B) of L2 reads per CTA instead of 32 KB.  The 2-CTA kernel is L2-bandwidth bound on B200
 // (5770 of ~6300 B/clk chip-wide at 1.41 PFLOP/s, profiles/r1_gemm_bench_v3_widths.txt), so bytes per flop is the lever.
-//   * TMA loads land on the issuing CTA's own full barrier (the multicast signals the same-offset barrier in both
-//     destinations); the non-leader CTA of a pair forwards "my stage is full" to its leader with a remote arrive;
+//   * every TMA load (unicast A, multicast B) is the cta_group::2 flavour: its bytes are reported to the pair leader of the
+//     destination CTA, so each leader waits on one barrier for the 64 KB of its pair (a first version forwarded the
+//     non-leader's barrier with a remote arrive per stage and ran at 40 % of the 2-CTA kernel);
 //   * a stage is reusable when BOTH pairs' MMAs have consumed it (the sibling pair's multicast writes into it), so every
 //     MMA commit arrives on the empty barrier of all four CTAs (count 2).
 // ---------------------------------------------------------------------------------------------------------------------
@@ -954,6 +955,13 @@ EPL_DEVICE void tma_load_2d_mcast(void* smem_dst, const void* desc, uint64_t* ba
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
       :: "r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+// same, cta_group::2 flavour: in every destination CTA the completion bytes are reported to the barrier at this offset in
+// that CTA's pair LEADER (peer bit cleared), so the leader's MMA thread waits on one barrier for both halves of its pair
+EPL_DEVICE void tma_load_2d_2cta_mcast(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      :: "r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1) : "memory");
 }
 EPL_DEVICE void umma_commit_mask(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -1024,17 +1032,17 @@ gemm4_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * kStageBytes;
           unsigned char* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);                       // A (own) + two quarters of B (one from each pair)
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);       // both CTAs of the pair: A + two quarters of B each
           const int k0 = kb * BLOCK_K;
           if (!p.a_mn_major) {
-            tma_load_2d(sa, &map_a, &full_bar[stage], k0, m0);
+            tma_load_2d_2cta(sa, &map_a, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
-            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * (BLOCK_K * 128), &map_a, &full_bar[stage], m0 + a * 64, k0);
+            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d_2cta(sa + a * (BLOCK_K * 128), &map_a, &full_bar[stage], m0 + a * 64, k0);
           }
           // quarter `pair` of the B tile: 64 of the 128 rows (K-major) / one 64-column swizzle atom (MN-major) = 8 KB
-          if (!p.b_mn_major) tma_load_2d_mcast(sb + pair * (64 * 128), &map_b, &full_bar[stage], k0, n0 + pair * 64, mask);
-          else tma_load_2d_mcast(sb + pair * (BLOCK_K * 128), &map_b, &full_bar[stage], n0 + pair * 64, k0, mask);
+          if (!p.b_mn_major) tma_load_2d_2cta_mcast(sb + pair * (64 * 128), &map_b, &full_bar[stage], k0, n0 + pair * 64, mask);
+          else tma_load_2d_2cta_mcast(sb + pair * (BLOCK_K * 128), &map_b, &full_bar[stage], n0 + pair * 64, k0, mask);
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
       }
@@ -1055,7 +1063,6 @@ gemm4_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const uint32_t tmem_d = tmem_base + acc * BN;
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(&full_bar[stage], phase);
-            mbar_wait_cluster(&peer_full[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * kStageBytes);
             const uint32_t sb = sa + kABytes;
@@ -1070,16 +1077,6 @@ gemm4_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             if (++stage == kStages2) { stage = 0; phase ^= 1; }
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-      } else {
-        // ================================ forwarder (non-leader): "my stage is full" -> leader ================================
-        int stage = 0; uint32_t phase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-          for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            mbar_arrive_leader_release(&peer_full[stage]);
-            if (++stage == kStages2) { stage = 0; phase ^= 1; }
-          }
         }
       }
     }

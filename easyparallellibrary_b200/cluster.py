@@ -172,6 +172,10 @@ class Cluster(object):
       if worker_index is None:
         worker_index = tindex
       self.ps_hosts = ",".join(spec.get("ps", [])) or self.ps_hosts
+      # epl-launch exports both TF_CONFIG (workers) and the torch.distributed variables (one rank per GPU); several workers
+      # may share a machine, so LOCAL_WORLD_SIZE counts the machine, not the worker: ranks per worker = WORLD_SIZE / workers
+      if gpus_per_worker is None and workers and "WORLD_SIZE" in env and int(env["WORLD_SIZE"]) % len(workers) == 0:
+        gpus_per_worker = int(env["WORLD_SIZE"]) // len(workers)
     if gpus_per_worker is None:
       gpus_per_worker = self.available_gpus()
     self.gpu_num_per_worker = max(int(gpus_per_worker), 1)

@@ -226,3 +226,20 @@ def test_throughput_meter_and_plan_summary():
   tr.build()
   text = plan_summary(tr)
   assert "stages=1" in text and "micro_batches=2" in text and "param group" in text
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_launcher_runs_a_two_process_job(tmp_path, amp):
+  """True multi-process job through ``epl-launch`` (reference: tests/Makefile:12-13 -> test_launcher.sh / test_amp_parallel.sh):
+  2 workers x 1 process on CPUs (gloo), a 2-layer MLP for 10 steps; success = exit code 0, identical replicas, and (amp) an
+  overflowing step skipped on every rank."""
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  cmd = [sys.executable, "-m", "easyparallellibrary_b200.utils.launcher", "--num_workers", "2", "--gpu_per_worker", "1", "--backend", "gloo",
+         "--log_dir", str(tmp_path), os.path.join(root, "tests", "scripts", "dnn_data_parallel.py")] + (["--amp"] if amp else [])
+  env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+  r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=300)
+  logs = "".join(open(os.path.join(tmp_path, f)).read()[-1500:] for f in sorted(os.listdir(tmp_path)))
+  assert r.returncode == 0, r.stdout[-1500:] + logs
+  assert r.stdout.count(" ok: ") == 2, r.stdout

@@ -27,12 +27,13 @@ epl.init(epl.Config({"amp.level": "bf16", "pipeline.num_micro_batch": args.micro
                      "cluster.colocate_split_and_replicate": args.tp > 1}))
 if args.tp > 1:
   epl.set_default_strategy(epl.replicate(device_count=1))
-model = Bert(BertConfig.named(args.size, num_pipeline_stages=args.stages, tensor_parallel=args.tp))
+bcfg = BertConfig.named(args.size, num_pipeline_stages=args.stages, tensor_parallel=args.tp)
+model = Bert(bcfg)
 loss_fn = squad_loss if args.stages > 1 else None
 trainer = epl.Trainer(model, "adamw", lr=3e-5, loss_fn=loss_fn)
 g = torch.Generator().manual_seed(0 if args.tp > 1 else int(os.environ.get("RANK", 0)))
 for step in range(args.steps):
-  ids = torch.randint(0, 30000, (args.batch, args.seq), generator=g)
+  ids = torch.randint(0, min(30000, bcfg.vocab_size), (args.batch, args.seq), generator=g)
   start, end = torch.randint(0, args.seq, (args.batch,), generator=g), torch.randint(0, args.seq, (args.batch,), generator=g)
   out = trainer.step(ids, start, end)
   if int(os.environ.get("RANK", 0)) == 0:

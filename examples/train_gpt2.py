@@ -37,7 +37,7 @@ trainer = epl.Trainer(model, "adamw", lr=1e-4, loss_fn=lm_loss if args.stages > 
 rank = int(os.environ.get("RANK", 0))
 g = torch.Generator().manual_seed(rank)
 for step in range(args.steps):
-  tokens = torch.randint(0, 50257, (args.batch * args.micro, args.seq), generator=g)
+  tokens = torch.randint(0, cfg.vocab_size, (args.batch * args.micro, args.seq), generator=g)
   out = trainer.step(tokens, tokens)
   if rank == 0:
     print("step %d loss %.4f" % (step, out.item()), flush=True)

@@ -21,7 +21,8 @@ def _torchrun(script_args, nproc, port, timeout=600):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("what,port", [("native", 29611), ("symm", 29612), ("fused", 29613), ("tp", 29614)])
 def test_mgpu_check(what, port):
-  n = min(torch.cuda.device_count(), 8)
+  # the fused data-parallel kernel was validated at 2 and 8 ranks; the other checks at 2 (round 1)
+  n = min(torch.cuda.device_count(), 8) if what == "fused" else 2
   r = _torchrun(["tools/mgpu_check.py", what], n, port)
   assert r.returncode == 0 and "MGPU CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 

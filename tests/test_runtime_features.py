@@ -243,3 +243,22 @@ def test_launcher_runs_a_two_process_job(tmp_path, amp):
   logs = "".join(open(os.path.join(tmp_path, f)).read()[-1500:] for f in sorted(os.listdir(tmp_path)))
   assert r.returncode == 0, r.stdout[-1500:] + logs
   assert r.stdout.count(" ok: ") == 2, r.stdout
+
+
+@pytest.mark.parametrize("script,argv", [
+    ("train_gpt2.py", ["--model", "tiny", "--batch", "2", "--seq", "32", "--steps", "2"]),
+    ("train_gpt2.py", ["--model", "tiny", "--batch", "2", "--seq", "32", "--steps", "2", "--zero", "v3", "--gc", "auto"]),
+    ("train_bert_pipeline.py", ["--size", "tiny", "--batch", "2", "--seq", "16", "--steps", "2"]),
+    ("train_moe.py", ["--batch", "2", "--seq", "16", "--steps", "2", "--experts", "4"]),
+])
+def test_example_scripts_run_on_cpu(script, argv):
+  """The examples (reference: examples/{bert,resnet,moe}) stay runnable: two steps of a tiny configuration on one CPU process."""
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="")
+  for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "TF_CONFIG"):
+    env.pop(k, None)
+  r = subprocess.run([sys.executable, os.path.join(root, "examples", script)] + argv, cwd=root, env=env, capture_output=True, text=True,
+                     timeout=600)
+  assert r.returncode == 0 and "step 1 loss" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]

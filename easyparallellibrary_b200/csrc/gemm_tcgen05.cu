@@ -18,8 +18,14 @@
 // B stored [K,N] — what the backward GEMMs dX = dY @ W and dW = dY^T @ X need), selected per
 // operand through the UMMA instruction descriptor + shared-memory descriptor.
 //
-// The reference has no GEMM of its own (all math is stock TF/cuBLAS); this kernel
-// is the compute half of the fused all-gather->GEMM / GEMM->reduce-scatter kernels (tp_fused.cu).
+// Three kernels share this file:
+//   gemm_tcgen05_kernel<BN, comm>  1-CTA tiles (described above); also the compute half of the fused collective modes
+//                                  COMM_AG (all-gather -> GEMM), COMM_RS (GEMM -> reduce-scatter), COMM_AGB (weight gather);
+//   gemm2_tcgen05_kernel           the default for M, N >= 256: CTA pairs (cta_group::2), 256 x {256,192,128} tiles,
+//                                  6-stage ring, 8 epilogue warps, aux-operand prefetch, red.add accumulation;
+//   gemm4_tcgen05_kernel           opt-in: 4-CTA clusters, two pairs sharing one multicast B tile.
+//
+// The reference has no GEMM of its own (all math is stock TF/cuBLAS).
 #include "epl_common.cuh"
 #include <algorithm>
 #include <cstdio>

@@ -21,6 +21,7 @@ _NCCL_DT = {torch.int8: 0, torch.uint8: 1, torch.int32: 2, torch.int64: 4, torch
             torch.float64: 8, torch.bfloat16: 9, torch.bool: 1}
 _NCCL_OP = {"sum": 0, "prod": 1, "max": 2, "min": 3, "avg": 4}
 _counter = {}          # per rank-set creation counter: identical on every member of the set
+_LIVE: list = []            # every open NativeBackend of this process
 
 
 def _find_nccl() -> str:
@@ -59,6 +60,13 @@ class NativeBackend(object):
     self.handle = h
     self.stream_ptr = self.lib.epl_comm_stream(h)
     self.stream = torch.cuda.ExternalStream(self.stream_ptr, device=device)
+    _LIVE.append(self)                      # the step watchdog aborts every live communicator on a hang
+
+  def abort(self) -> None:
+    """``ncclCommAbort``: unblocks kernels of this communicator that wait for a dead peer (used by runtime/watchdog.py;
+    the reference wraps Abort but never calls it, tensorflow_nccl.h:119-123)."""
+    if getattr(self, "handle", None):
+      self.lib.epl_comm_abort(self.handle)
 
   def _check(self, rc: int, what: str) -> None:
     if rc != 0:
@@ -192,3 +200,5 @@ class NativeBackend(object):
       self.stream = None
       self.lib.epl_comm_destroy(self.handle)
       self.handle = None
+      if self in _LIVE:
+        _LIVE.remove(self)

@@ -262,3 +262,30 @@ def test_example_scripts_run_on_cpu(script, argv):
   r = subprocess.run([sys.executable, os.path.join(root, "examples", script)] + argv, cwd=root, env=env, capture_output=True, text=True,
                      timeout=600)
   assert r.returncode == 0 and "step 1 loss" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
+
+
+def test_step_watchdog_and_timeline_hook(tmp_path):
+  """Failure detection (runtime/watchdog.py) and the kernel/operator timeline hook (profiler/timeline.py)."""
+  import time
+  from easyparallellibrary_b200.profiler.timeline import TimelineHook
+  from easyparallellibrary_b200.runtime.watchdog import StepWatchdog
+  fired = []
+  dog = StepWatchdog(timeout_s=0.15, on_timeout=lambda step, elapsed: fired.append((step, elapsed)), poll_s=0.02)
+  try:
+    dog.before_step(None); time.sleep(0.05); dog.after_step(None, None)          # a healthy step
+    assert not fired
+    dog.before_step(None); time.sleep(0.4)                                       # a hung step fires exactly once
+    assert len(fired) == 1 and fired[0][0] == 1 and fired[0][1] > 0.15
+    dog.after_step(None, None)
+  finally:
+    dog.close()
+  epl.init(init_process_group=False)
+  with epl.replicate(1):
+    model = nn.Sequential(nn.Linear(16, 32), nn.Tanh(), nn.Linear(32, 4))
+  tr = epl.Trainer(model, "adamw", lr=1e-3, loss_fn=lambda y, t: nn.functional.cross_entropy(y, t))
+  hook = TimelineHook(output_dir=str(tmp_path), start_step=1, steps=2)
+  tr.hooks.append(hook)
+  for _ in range(4):
+    tr.step(torch.randn(8, 16), torch.randint(0, 4, (8,)))
+  text = open(os.path.join(tmp_path, "kernel_table.txt")).read()
+  assert "timeline: span" in text and hook.by_name and any("addmm" in k or "linear" in k or "mm" in k for k in hook.by_name)

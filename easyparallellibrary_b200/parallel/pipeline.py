@@ -210,6 +210,9 @@ class PipelineExecutor(object):
       else:
         torch.autograd.backward(y, grad_tensors=torch.zeros_like(y))
     Graph.get().pop_collections()
+    for z in getattr(tr, "zero3", {}).values():
+      z.finish_backward()
+      z.zero_grad()
     for flat in tr.flats.values():
       flat.zero_grad()
     with torch.no_grad():

@@ -289,3 +289,16 @@ def test_step_watchdog_and_timeline_hook(tmp_path):
     tr.step(torch.randn(8, 16), torch.randint(0, 4, (8,)))
   text = open(os.path.join(tmp_path, "kernel_table.txt")).read()
   assert "timeline: span" in text and hook.by_name and any("addmm" in k or "linear" in k or "mm" in k for k in hook.by_name)
+
+
+def test_bench_reference_arm_reports_unavailable():
+  """bench.py contract: the reference (TensorFlow 1.15) cannot be installed offline, so `--impl reference` prints one JSON line with
+  `unavailable` and exits 0."""
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "3"],
+                     cwd=root, capture_output=True, text=True, timeout=120)
+  assert r.returncode == 0
+  line = json.loads(r.stdout.strip().splitlines()[-1])
+  assert line["impl"] == "reference" and "unavailable" in line

@@ -17,7 +17,7 @@ from easyparallellibrary_b200.config import Config
 from easyparallellibrary_b200.env import Env
 from easyparallellibrary_b200.cluster import Cluster, VirtualDevice, Device
 from easyparallellibrary_b200.ir.graph import (Graph, GraphKeys, add_to_collection, get_collection,
-                                               get_all_collections)
+                                               get_all_collections, current_micro_batch)
 from easyparallellibrary_b200.ir.phase import ModelPhase
 from easyparallellibrary_b200.strategies import replicate, split, Replicate, Split
 

@@ -80,6 +80,7 @@ class Graph(object):
     self._nodes: List[Node] = []
     self.training = True
     self.parallel_information: Dict[str, Any] = {}
+    self.current_micro_batch = None      # the (inputs, *targets) tuple of the micro-batch being executed, on every stage
 
   # ------------------------------------------------------------------ access
   @staticmethod
@@ -268,3 +269,14 @@ def get_collection(key: str):
 
 def get_all_collections():
   return Graph.get().get_all_collections()
+
+
+def current_micro_batch():
+  """The ``(inputs, *targets)`` tuple of the micro-batch whose forward is running, or ``None`` outside a training step.
+
+  Under pipeline parallelism only one tensor travels between stages, but every stage is handed the whole micro-batch, so a
+  later stage reads side inputs (sequence length, masks, position ids) from here instead of re-deriving them from the
+  activation (the reference gets this for free: every stage subgraph sees the same input tensors of its micro-batch clone,
+  ``graph_editor.py:397-421``)."""
+  g = Graph.get(may_create=False)
+  return None if g is None else g.current_micro_batch

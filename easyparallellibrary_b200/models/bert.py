@@ -102,12 +102,47 @@ class BertLayerTP(nn.Module):
 
   def forward(self, x_shard):                      # [T/N, d]
     S = self.seq_len
+    if S is None:                                  # a later pipeline stage: the sequence length comes from the micro-batch
+      import easyparallellibrary_b200 as epl
+      S = epl.current_micro_batch()[0].shape[1]
     qkv = self.qkv(x_shard)                        # [T, 3d/N]  (all-gather -> GEMM)
     T = qkv.shape[0]
     from easyparallellibrary_b200.ops.attention import attention_packed
     a = attention_packed(qkv.view(T // S, S, 3, self.heads_local, self.head_dim), causal=False).reshape(T, -1)
     x_shard = self.ln1(x_shard + self.proj(a))     # GEMM -> reduce-scatter
     return self.ln2(x_shard + self.out(self.fc(x_shard)))
+
+
+class _TokenShard(nn.Module):
+  """[B, S, d] -> this TP rank's token shard [B*S/N, d] (every rank of the split group holds the same batch)."""
+
+  def __init__(self, split):
+    super().__init__()
+    self.split = split
+
+  def forward(self, x):
+    from easyparallellibrary_b200.ops.tensor_parallel import current_tp_group
+    g = current_tp_group(self.split)
+    B, S, d = x.shape
+    return x.reshape(B * S, d).chunk(g.size, 0)[g.rank].contiguous()
+
+
+class _TokenGather(nn.Module):
+  """Token shard [B*S/N, d] -> [B, S, d] (all-gather forward, reduce-scatter backward)."""
+  epl_collective = True
+
+  def __init__(self, split):
+    super().__init__()
+    self.split = split
+
+  def forward(self, x):
+    import easyparallellibrary_b200 as epl
+    from easyparallellibrary_b200.ops.tensor_parallel import current_tp_group
+    g = current_tp_group(self.split)
+    ids = epl.current_micro_batch()[0]
+    B, S = ids.shape[0], ids.shape[1]
+    full = _gather_tokens(x, g) if x.requires_grad else g.comm.allgather(x)
+    return full.view(B, S, -1)
 
 
 class SquadHead(nn.Module):
@@ -137,35 +172,33 @@ class Bert(nn.Module):
     self.embed = BertEmbeddings(cfg)
     layers = []
     self._split = epl.split(device_count=cfg.tensor_parallel) if cfg.tensor_parallel > 1 else None
+    # tensor parallel: the token sharding / gathering are blocks of their own, so a pipeline cut can fall anywhere between
+    # layers and every stage still sees [tokens/N, d] activations (stage 0 owns the shard block, the last stage the gather)
+    self.shard = _TokenShard(self._split) if self._split is not None else None
     for i in range(cfg.num_hidden_layers):
       if stages > 1 and i > 0 and i % per == 0:
         epl.set_default_strategy(epl.replicate(1, name="stage_%d" % (i // per)))
       layers.append(BertLayerTP(cfg, self._split) if self._split is not None else BertLayer(cfg))
     self.layers = nn.ModuleList(layers)
+    self.gather = _TokenGather(self._split) if self._split is not None else None
     self.head = SquadHead(cfg)
 
   def epl_sequential(self):
-    return [self.embed] + list(self.layers) + [self.head]
+    tp_in = [self.shard] if self.shard is not None else []
+    tp_out = [self.gather] if self.gather is not None else []
+    return [self.embed] + tp_in + list(self.layers) + tp_out + [self.head]
 
   def forward(self, ids, start=None, end=None):
-    x = self.embed(ids)
-    B, S, d = x.shape
-    if self._split is not None:
-      from easyparallellibrary_b200.ops.tensor_parallel import current_tp_group
-      g = current_tp_group(self._split)
-      x = x.reshape(B * S, d)
-      x = x.chunk(g.size, 0)[g.rank].contiguous()          # token shard (every TP rank holds the same batch)
-      for l in self.layers:
-        l.seq_len = S
-        x = l(x)
-      x = g.comm.allgather(x).view(B, S, d) if not x.requires_grad else _gather_tokens(x, g).view(B, S, d)
-    else:
-      for l in self.layers:
-        x = l(x)
-    logits = self.head(x)
+    import easyparallellibrary_b200 as epl
+    from easyparallellibrary_b200.ir.graph import Graph
+    if epl.current_micro_batch() is None:                   # called outside a Trainer step (plain module use)
+      Graph.get().current_micro_batch = (ids, start, end)
+    x = ids
+    for block in self.epl_sequential():
+      x = block(x)
     if start is None:
-      return logits
-    return squad_loss(logits, start, end)
+      return x
+    return squad_loss(x, start, end)
 
 
 def _gather_tokens(x, g):

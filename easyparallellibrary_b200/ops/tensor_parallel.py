@@ -43,6 +43,16 @@ class TPGroup(object):
   @property
   def comm(self):
     if self._comm is None:
+      # dist.new_group is collective over the WORLD and order sensitive.  With several tensor-parallel groups (split(n) on
+      # k*n GPUs = k groups that are data-parallel replicas of each other) every rank must create every group, in the same
+      # order, before it picks its own — otherwise ranks [0,1] and [2,3] call new_group with different lists and deadlock.
+      from easyparallellibrary_b200.communicators.backend import register_groups
+      import torch.distributed as dist
+      if dist.is_available() and dist.is_initialized() and self.size > 1:
+        world = dist.get_world_size()
+        if world > self.size and world % self.size == 0:
+          copies = 1                                   # the "simple" communicator kind owns a single transport
+          register_groups([list(range(b, b + self.size)) for b in range(0, world, self.size)], copies=copies)
       self._comm = get_or_create("TENSOR_PARALLEL", self.ranks, kind="simple")
     return self._comm
 

@@ -432,6 +432,7 @@ class Trainer(object):
       for i, mb in enumerate(micro):
         self._first_micro_batch = i == 0
         self._last_micro_batch = i == M - 1
+        graph.current_micro_batch = mb
         with phase_scope(ModelPhase.FORWARD):
           loss = self._forward_loss(mb, kwargs)
         collected.append(graph.pop_collections())
@@ -450,6 +451,7 @@ class Trainer(object):
     if losses:
       out.loss = torch.stack([l.float() for l in losses]).mean() if mean else torch.stack([l.float() for l in losses]).sum()
     out.collections = self._merge_collections(collected)
+    graph.current_micro_batch = None
     for h in self.hooks:
       h.after_step(self, out)
     return out
@@ -635,6 +637,7 @@ class Trainer(object):
     batch = tuple(_to_device(x, self.device) for x in batch)
     was = self.model.training
     self.model.eval()
+    Graph.get().current_micro_batch = batch
     try:
       if self.plan.pipeline:
         return self.pipe.forward_only(batch)

@@ -197,6 +197,7 @@ class PipelineExecutor(object):
       x = torch.zeros(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
       if x.is_floating_point():
         x.requires_grad_()
+    Graph.get().current_micro_batch = mb
     with phase_scope(ModelPhase.FORWARD):
       y = self.module(x)
       if self.last and tr.loss_fn is not None:
@@ -253,6 +254,7 @@ class PipelineExecutor(object):
         recv_b[ins.mb] = (buf, self.p2p.recv_bwd(buf))
       elif ins.op == S.F:
         mb = micro[ins.mb]
+        graph.current_micro_batch = mb
         if self.first:
           x = mb[0]
         else:
@@ -307,6 +309,7 @@ class PipelineExecutor(object):
   @torch.no_grad()
   def forward_only(self, batch: Tuple[Any, ...]):
     """Evaluation: stages run back to back, no micro-batching."""
+    Graph.get().current_micro_batch = batch
     if self.first:
       x = batch[0]
     else:

@@ -192,3 +192,32 @@ def test_expert_parallel_moe_matches_unsharded():
   got_wo = np.concatenate([res[0][3], res[1][3]], 0)
   np.testing.assert_allclose(got_wi, wi_g.numpy(), rtol=1e-4, atol=1e-5)
   np.testing.assert_allclose(got_wo, wo_g.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def _tp2_dp2_worker(rank, world):
+  """split(2) on 4 ranks = two tensor-parallel groups [0,1] and [2,3] that are data-parallel replicas of each other."""
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.models.bert import Bert, BertConfig
+  epl.init(epl.Config({"cluster.colocate_split_and_replicate": True}))
+  epl.set_default_strategy(epl.replicate(device_count=1))
+  torch.manual_seed(0)
+  model = Bert(BertConfig.named("tiny", tensor_parallel=2))
+  tr = epl.Trainer(model, "sgd", lr=0.1)
+  g = torch.Generator().manual_seed(rank // 2)        # one batch per TP group, different between the groups
+  losses = []
+  for _ in range(3):
+    ids = torch.randint(0, 1000, (4, 16), generator=g)
+    s, e = torch.randint(0, 16, (4,), generator=g), torch.randint(0, 16, (4,), generator=g)
+    losses.append(float(tr.step(ids, s, e).loss))
+  flat = torch.cat([p.detach().float().flatten() for p in model.parameters()])
+  return flat.numpy(), losses
+
+
+def test_two_tensor_parallel_groups_are_data_parallel_replicas():
+  """TP x DP hybrid: every rank creates both TP process groups collectively (a lazy per-group new_group deadlocks), sharded
+  weights are reduced across the groups (ranks 0/2 and 1/3 stay bit-identical), replicated weights across all four."""
+  res = run_distributed(_tp2_dp2_worker, 4)
+  np.testing.assert_array_equal(res[0][0], res[2][0])
+  np.testing.assert_array_equal(res[1][0], res[3][0])
+  assert res[0][1] == res[1][1] and res[2][1] == res[3][1] and res[0][1] != res[2][1]   # the loss is per TP group
+  assert not np.array_equal(res[0][0], res[1][0])                                        # different shards of the sharded weights

@@ -47,6 +47,34 @@ def _sym_lib():
   return lib
 
 
+_EXCHANGES: dict = {}     # per rank-set exchange counter: identical on every member (buffers are created in program order)
+
+
+def _exchange_handles(raw: bytes, ranks: Sequence[int], my_index: int, group=None) -> List[bytes]:
+  """All-gather of the 64-byte IPC handles among ``ranks``.
+
+  Goes through the rendezvous store (each member publishes under a key unique to (rank set, creation index, member) and
+  reads the others'), NOT through a process-group collective: the rank set is often a strict subset of the world (the
+  data-parallel group of one pipeline stage, one of several tensor-parallel groups) whose communicator is an in-tree NCCL
+  communicator without a torch ProcessGroup, and a WORLD collective would need every rank of the job to create the same
+  number of buffers at the same time.  Falls back to ``all_gather_object`` over ``group`` when no store is available."""
+  tag = "-".join(str(int(r)) for r in ranks)
+  n = _EXCHANGES.get(tag, 0)
+  _EXCHANGES[tag] = n + 1
+  store = None
+  try:
+    store = dist.distributed_c10d._get_default_store()
+  except Exception:  # pragma: no cover
+    store = None
+  if store is None:                                      # pragma: no cover
+    out: List[Optional[bytes]] = [None] * len(ranks)
+    dist.all_gather_object(out, raw, group=group)
+    return out  # type: ignore[return-value]
+  base = "epl_symm/%s/%d/" % (tag, n)
+  store.set(base + str(my_index), raw)
+  return [raw if i == my_index else bytes(store.get(base + str(i))) for i in range(len(ranks))]
+
+
 class SymmetricBuffer(object):
   def __init__(self, nbytes: int, ranks: Sequence[int], device: torch.device, group=None):
     self.lib = _sym_lib()
@@ -68,8 +96,7 @@ class SymmetricBuffer(object):
       rc = self.lib.epl_symm_export(ctypes.c_void_p(self.local_ptr), h)
       if rc:
         raise RuntimeError("cudaIpcGetMemHandle failed (%d)" % rc)
-      handles: List[Optional[bytes]] = [None] * self.world
-      dist.all_gather_object(handles, h.raw, group=group)
+      handles = _exchange_handles(h.raw, self.ranks, self.rank, group)
       for r, raw in enumerate(handles):
         if r == self.rank:
           continue

@@ -258,3 +258,24 @@ def test_zero3_two_ranks_parameters_match_and_are_released():
   for out, resident in res:
     assert resident == 0                                  # nothing materialised between steps
     assert _max_diff(base[1], out) < 1e-6
+
+
+def _handle_exchange_worker(rank, world):
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.runtime.symmetric import _exchange_handles
+  epl.init()                                       # joins the gloo process group (and with it the rendezvous store)
+  ranks = [0, 1] if rank < 2 else [2, 3]
+  outs = []
+  for k in range(3 if rank < 2 else 1):          # subset [0,1] creates three buffers, subset [2,3] only one
+    raw = bytes([rank, k]) * 32
+    outs.append(_exchange_handles(raw, ranks, ranks.index(rank)))
+  return [[list(b[:2]) for b in o] for o in outs]
+
+
+def test_symmetric_handle_exchange_over_rank_subsets():
+  """The IPC-handle exchange of NVLink symmetric buffers must work for strict subsets of the world that create different
+  numbers of buffers (the data-parallel group of each pipeline stage, one of several tensor-parallel groups): it goes
+  through the rendezvous store, not a WORLD collective."""
+  res = run_distributed(_handle_exchange_worker, 4)
+  assert res[0] == [[[0, k], [1, k]] for k in range(3)] and res[1] == res[0]
+  assert res[2] == [[[2, 0], [3, 0]]] and res[3] == res[2]

@@ -206,6 +206,55 @@ def check_tp(dev, world, rank):
     json.dump({"%d_%d_%d_%s_%s" % k: v for k, v in results.items()}, open("gpurun_out/tp_fused_bench_w%d.json" % world, "w"))
 
 
+def check_moe(dev, world, rank):
+  """K5: the peer-store all-to-all (csrc/symm.cu alltoall_p2p_kernel) vs the NCCL all-to-all, values and timing; then the
+  expert-parallel MoE layer forward/backward with either transport."""
+  from easyparallellibrary_b200.ops import moe
+  from easyparallellibrary_b200.ops import tensor_parallel as tp
+  epl.init(epl.Config({"cluster.colocate_split_and_replicate": True}))
+  with epl.split(world):
+    group = tp.current_tp_group()
+  torch.manual_seed(11 + rank)
+  for rows in (world * 64, world * 4096):
+    t = torch.randn(rows, 512, device=dev).bfloat16()
+    outs = {}
+    for p2p in (False, True):
+      moe.USE_P2P_KERNEL = p2p
+      for _ in range(3):                                  # repeated calls exercise the epoch / buffer-reuse protocol
+        outs[p2p] = moe.expert_all_to_all_raw(t, group)
+      torch.cuda.synchronize()
+    diff = (outs[True].float() - outs[False].float()).abs().max().item()
+    times = {}
+    for p2p in (False, True):
+      moe.USE_P2P_KERNEL = p2p
+      torch.cuda.synchronize(); dist.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(10):
+        moe.expert_all_to_all_raw(t, group)
+      e1.record(); torch.cuda.synchronize()
+      times[p2p] = e0.elapsed_time(e1) / 10
+    log("all-to-all %d x 512 bf16: |p2p - nccl| = %.1e ; nccl %.3f ms, p2p kernel %.3f ms" % (rows, diff, times[False], times[True]))
+    assert diff == 0.0
+  moe.USE_P2P_KERNEL = True
+  torch.manual_seed(5)
+  with epl.split(world):
+    layer = moe.MoEFFN(256, 512, 2 * world, capacity_factor=2.0).to(dev)
+  res = {}
+  for p2p in (False, True):
+    moe.USE_P2P_KERNEL = p2p
+    torch.manual_seed(100 + rank)
+    x = torch.randn(2, 64, 256, device=dev, requires_grad=True)
+    y = layer(x)
+    layer.zero_grad()
+    (y.square().sum() + layer.aux_loss).backward()
+    res[p2p] = (y.detach().clone(), x.grad.clone(), layer.wi.grad.clone())
+  d = max((a - b).abs().max().item() for a, b in zip(res[True], res[False]))
+  log("MoE layer fwd/bwd with p2p vs nccl transport: max diff %.2e" % d)
+  assert d < 1e-5
+  moe.USE_P2P_KERNEL = True
+
+
 def main():
   dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
   rank, world = dist.get_rank(), dist.get_world_size()
@@ -220,6 +269,8 @@ def main():
     check_fused(dev, world, rank)
   if "tp" in what:
     check_tp(dev, world, rank)
+  if "moe" in what:
+    check_moe(dev, world, rank)
   dist.barrier()
   log("MGPU CHECK PASSED")
   dist.destroy_process_group()

@@ -21,7 +21,10 @@ from torch import nn
 
 from easyparallellibrary_b200.communicators import functional as CF
 
-USE_P2P_KERNEL = True
+# The peer-store all-to-all kernel has not been exercised on hardware yet (tools/mgpu_check.py moe is the check); until it
+# has, NCCL grouped send/recv is the default transport and EPL_MOE_P2P=1 opts in.
+import os as _os
+USE_P2P_KERNEL = _os.environ.get("EPL_MOE_P2P", "0") == "1"
 _A2A_WS: Dict[int, "_A2AWorkspace"] = {}
 
 

@@ -184,19 +184,11 @@ def main():
       run(2, False)
       torch.cuda.synchronize()
     if rank == 0:
+      from easyparallellibrary_b200.profiler.timeline import kernel_table
+      text, _ = kernel_table(prof.events())
       evs = [e for e in prof.events() if e.device_type.name == "CUDA"]
-      span = (max(e.time_range.end for e in evs) - min(e.time_range.start for e in evs)) / 1e3
-      agg = {}
-      for e in evs:
-        a = agg.setdefault(e.name, [0.0, 0])
-        a[0] += e.time_range.elapsed_us() / 1e3
-        a[1] += 1
-      busy = sum(v[0] for v in agg.values())
       with open(args.profile, "w") as f:
-        f.write("2 steps: GPU span %.2f ms, sum of kernel time %.2f ms (%.1f%% busy, streams may overlap), %d kernels\n" % (
-            span, busy, 100.0 * busy / span, sum(v[1] for v in agg.values())))
-        for name, (ms_k, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
-          f.write("%6.2f%% %9.3f ms %6d  %s\n" % (100.0 * ms_k / busy, ms_k, n, name[:110]))
+        f.write(text)
         # GEMM durations in launch order (first profiled step): 48 x [qkv, proj, fc1, fc2] forward, lm_head, then backward
         gem = sorted((e.time_range.start, e.time_range.elapsed_us()) for e in evs if "gemm" in e.name)
         gem = gem[:len(gem) // 2]

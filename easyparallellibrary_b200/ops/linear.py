@@ -181,9 +181,55 @@ def _use_kernel(x: torch.Tensor, w: torch.Tensor) -> bool:
           and x.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0 and w.is_contiguous())
 
 
+class _GatherLinearFn(torch.autograd.Function):
+  """``linear`` whose weight is a ZeRO-3 shard with a deferred all-gather (``parallel/zero3.py::PendingGather``): the forward
+  GEMM gathers the weight over NVLink while it multiplies (K2, ``ops/tp_kernels.ag_weight_gemm``); backward is the ordinary
+  pair of GEMMs on the weight the ZeRO-3 engine re-gathers before the layer's backward."""
+
+  @staticmethod
+  def forward(ctx, x, w, bias, gelu, pend):
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+      x2 = x2.contiguous()
+    y, pre = pend.gemm(x2, bias, gelu)                      # fills w's storage as a side effect
+    ctx.save_for_backward(x2, w, pre if pre is not None else x2.new_empty(0))
+    ctx.has_bias, ctx.gelu, ctx.xshape, ctx.has_res = bias is not None, gelu, x.shape, False
+    return y.view(*x.shape[:-1], w.shape[0])
+
+  @staticmethod
+  def backward(ctx, dy):
+    x2, w, pre = ctx.saved_tensors
+    if x2.is_cuda and _lib.available():
+      return _LinearFn.backward(ctx, dy)
+    dy2 = dy.reshape(-1, dy.shape[-1])                      # reference math (CPU tests of the protocol)
+    if ctx.gelu:
+      with torch.enable_grad():
+        pr = pre.detach().requires_grad_()
+        torch.nn.functional.gelu(pr, approximate="tanh").backward(dy2)
+      dy2 = pr.grad
+    dx = (dy2 @ w).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+    dw = dy2.t() @ x2 if ctx.needs_input_grad[1] else None
+    db = dy2.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+    return dx, dw, db, None, None
+
+
+def _resolve_pending(x: torch.Tensor, w: torch.Tensor, fusable: bool):
+  """ZeRO-3 deferred gather: returns the pending object if the fused weight-gather GEMM should run, else gathers now."""
+  pend = getattr(w, "epl_pending_gather", None)
+  if pend is None:
+    return None
+  if fusable and pend.can_fuse(x):
+    return pend
+  pend.materialize()
+  return None
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False,
            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
   """``y = x @ w^T (+ bias) (GELU)`` or, with ``residual``, ``y = residual + x @ w^T + bias`` — one kernel either way."""
+  pend = _resolve_pending(x, w, fusable=residual is None)
+  if pend is not None:
+    return _GatherLinearFn.apply(x, w, bias, gelu, pend)
   if _use_kernel(x, w):
     return _LinearFn.apply(x, w, bias, gelu, residual)
   y = torch.nn.functional.linear(x, w, bias)
@@ -193,6 +239,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def mlp(x, w1, b1, w2, b2, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+  _resolve_pending(x, w1, fusable=False)          # the fused MLP block keeps its own kernels: gather a deferred weight first
   if _use_kernel(x, w1) and w2.shape[0] % 8 == 0:
     return _MlpFn.apply(x, w1, b1, w2, b2, residual)
   h = torch.nn.functional.gelu(torch.nn.functional.linear(x, w1, b1), approximate="tanh")

@@ -115,11 +115,12 @@ def gemm_rs(a: torch.Tensor, w: torch.Tensor, group, b_mn_major: bool = False) -
   return out
 
 
-def ag_weight_gemm(x2: torch.Tensor, w_shard: torch.Tensor, group, bias=None, gelu: bool = False):
+def ag_weight_gemm(x2: torch.Tensor, w_shard: torch.Tensor, group, bias=None, gelu: bool = False, out_w_full: Optional[torch.Tensor] = None):
   """K2 — ZeRO-3 weight all-gather fused with the GEMM that consumes it.
 
   ``w_shard``: this rank's ``[N/world, K]`` rows of the weight.  Returns ``(y, pre, w_full)`` with
-  ``y = x2 @ gather(w_shard)^T (+bias)(gelu)``; the gathered weight is kept for the backward GEMMs.
+  ``y = x2 @ gather(w_shard)^T (+bias)(gelu)``; the gathered weight is kept for the backward GEMMs (written into
+  ``out_w_full`` — the ZeRO-3 unit's transient buffer — when given).
   """
   from easyparallellibrary_b200.ops import linear as L
   lib = _lib_fused()
@@ -138,7 +139,12 @@ def ag_weight_gemm(x2: torch.Tensor, w_shard: torch.Tensor, group, bias=None, ge
     torch.cuda.synchronize(x2.device)
     ws.wshard = SymmetricBuffer(max(nbytes, 1 << 20), group.ranks, x2.device, group=ws.pg)
   ws.wshard.tensor(w_shard.dtype, rows * K).copy_(w_shard.reshape(-1))
-  w_full = torch.empty((N, K), dtype=w_shard.dtype, device=x2.device)
+  if out_w_full is not None:
+    if out_w_full.numel() != N * K or out_w_full.dtype != w_shard.dtype or not out_w_full.is_contiguous():
+      raise ValueError("ag_weight_gemm: out_w_full must be a contiguous [N, K] buffer of the weight dtype")
+    w_full = out_w_full.view(N, K)
+  else:
+    w_full = torch.empty((N, K), dtype=w_shard.dtype, device=x2.device)
   y = torch.empty((M, N), dtype=x2.dtype, device=x2.device)
   pre = torch.empty_like(y) if gelu else None
   epi = L.EPI_BIAS_GELU if gelu else (L.EPI_BIAS if bias is not None else L.EPI_NONE)

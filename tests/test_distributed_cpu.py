@@ -279,3 +279,60 @@ def test_symmetric_handle_exchange_over_rank_subsets():
   res = run_distributed(_handle_exchange_worker, 4)
   assert res[0] == [[[0, k], [1, k]] for k in range(3)] and res[1] == res[0]
   assert res[2] == [[[2, 0], [3, 0]]] and res[3] == res[2]
+
+
+def _zero3_fused_gather_worker(rank, world, fused):
+  """ZeRO-3 on a stack of layers built from ops.linear.Linear; with ``fused`` the first GEMM weight of every layer defers its
+  all-gather into the GEMM (K2 protocol), emulated here by all-gather + matmul behind the implementation hook."""
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.ops.linear import Linear
+  from easyparallellibrary_b200.parallel import zero3
+  calls = [0]
+
+  def emulate(x2, w_shard, group, bias=None, gelu=False, out_w_full=None):
+    calls[0] += 1
+    full = group.comm.allgather(w_shard.contiguous())             # [N, K] rows in rank order
+    out_w_full.view_as(full).copy_(full)
+    pre = torch.nn.functional.linear(x2, full, bias)
+    return (torch.nn.functional.gelu(pre, approximate="tanh"), pre, full) if gelu else (pre, None, full)
+
+  zero3.GATHER_GEMM_IMPL = emulate if fused else None
+
+  class Layer(nn.Module):
+    def __init__(self, d, h, gelu):
+      super().__init__()
+      self.norm = nn.LayerNorm(d)
+      self.up = Linear(d, h, gelu=gelu)                    # first GEMM: deferred gather (h % world == 0)
+      self.down = Linear(h, d)
+
+    def forward(self, x):
+      return x + self.down(self.up(self.norm(x)))
+
+  epl.init(epl.Config({"zero.level": "v3"}))
+  torch.manual_seed(0)
+  with epl.replicate(1):
+    model = nn.Sequential(Layer(16, 32, True), Layer(16, 24, False), nn.Linear(16, 1))
+  tr = epl.Trainer(model, "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2).build()
+  z = tr.zero3[0]
+  deferred = sum(1 for u in z.units if u.deferred)
+  torch.manual_seed(1)
+  X, Y = torch.randn(4, 8, 16), torch.randn(4, 8, 1)
+  losses = [float(tr.step(X[i].chunk(world)[rank], Y[i].chunk(world)[rank]).loss) for i in range(4)]
+  z.gather_all()
+  out = [p.detach().float().numpy().copy() for p in model.parameters()]
+  z.release_all()
+  zero3.GATHER_GEMM_IMPL = None
+  return out, losses, calls[0], deferred
+
+
+def test_zero3_deferred_weight_gather_matches_plain_zero3():
+  """K2 integration: the weight of a layer's first GEMM is gathered inside that GEMM (parallel/zero3.py::PendingGather ->
+  ops.linear._GatherLinearFn).  Same parameters and losses as ZeRO-3 with ordinary all-gathers, and the fused path really ran:
+  2 deferred units x 4 steps forward (the backward re-gathers through the library path)."""
+  plain = run_distributed(_zero3_fused_gather_worker, 2, args=(False,))
+  fused = run_distributed(_zero3_fused_gather_worker, 2, args=(True,))
+  assert plain[0][3] == 0 and fused[0][3] == 2 and plain[0][2] == 0 and fused[0][2] == 8
+  for r in range(2):
+    np.testing.assert_allclose(fused[r][1], plain[r][1], rtol=1e-5, atol=1e-6)
+    for a, b in zip(fused[r][0], plain[r][0]):
+      np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)

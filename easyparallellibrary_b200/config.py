@@ -47,6 +47,8 @@ _opt("gradient_checkpoint", "type", "", "'' | collection | auto.")
 _opt("gradient_checkpoint", "end_taskgraph", -1, "Last taskgraph that auto checkpointing may touch.")
 _opt("gradient_checkpoint", "check_gradients", False, "Validate recompute gradients against plain ones.")
 _opt("zero", "level", "", "'' | v0 | v1 | v2 | v3.")
+_opt("zero", "fused_gather", False,
+     "B200 extension (v3): gather the weight of a layer's first GEMM inside that GEMM instead of before it.")
 _opt("offload", "level", "", "'' | v0 (weights and optimizer state live on the host).")
 _opt("amp", "level", "", "'' | O1 (fp16 + loss scale) | bf16.")
 _opt("amp", "debug_log", False, "Log the precision decision for every module.")

@@ -29,7 +29,8 @@ from easyparallellibrary_b200.runtime.optimizer import FlatOptimizer
 # resolves the tag by running the fused weight-gather GEMM (``ops/tp_kernels.ag_weight_gemm``), which fills the buffer over
 # NVLink while it multiplies, or — whenever the fused kernel does not apply (CPU, residual epilogue, unsupported dtype) — by a
 # plain all-gather.  ``GATHER_GEMM_IMPL`` is the implementation hook: ``None`` = pick the kernel on eligible GPUs; the CPU
-# tests install an emulation to exercise the protocol.  Off by default until the integrated path has run on hardware.
+# tests install an emulation to exercise the protocol.  Off by default (``zero.fused_gather`` /
+# ``EPL_ZERO3_FUSED_GATHER=1``) until the integrated path has run on hardware.
 FUSE_FIRST_GEMM = os.environ.get("EPL_ZERO3_FUSED_GATHER", "0") == "1"
 GATHER_GEMM_IMPL = None
 
@@ -168,7 +169,7 @@ class Zero3Engine(object):
         seen.add(id(p))
       if not ps:
         continue
-      first = self._first_gemm_weight(m, ps) if (FUSE_FIRST_GEMM or GATHER_GEMM_IMPL is not None) else None
+      first = self._first_gemm_weight(m, ps) if (cfg.zero.fused_gather or FUSE_FIRST_GEMM or GATHER_GEMM_IMPL is not None) else None
       groups = [([first], True), ([p for p in ps if p is not first], False)] if first is not None else [(ps, False)]
       for plist, deferred in groups:
         if not plist:

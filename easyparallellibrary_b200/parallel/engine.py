@@ -395,7 +395,7 @@ class Trainer(object):
         p.grad = view if view.dtype == p.dtype else None
     b.ready += 1
     if self._last_micro_batch and b.ready % len(b.params) == 0:
-      if self.fused is not None and self.fused.overlap and not self.plan.pipeline:
+      if self.fused is not None and self.fused.overlap and not self.plan.pipeline and self.max_grad_norm is None:
         self.fused.launch_bucket_async(s, b.index, self._mean and not self.has_split)
       elif self._overlap:
         self._launch_bucket_reduce(s, b)
@@ -487,8 +487,6 @@ class Trainer(object):
     clip_after = cfg.communication.clip_after_allreduce
     inv = self.scaler.inv_scale
     gnorm = None
-    if self.fused is not None:
-      return self.fused.reduce_and_apply(mean)
     # (1) clip-then-reduce: local norm, local clip coefficient folded into the grad scale
     local_coef = 1.0
     if self.max_grad_norm is not None and not clip_after:
@@ -498,6 +496,9 @@ class Trainer(object):
         for s_ in self.group_keys:
           for g_ in self.flats[s_].flat_grads.values():
             g_.mul_(c)
+    if self.fused is not None:          # the gradient buckets live in symmetric memory: the fused kernel reads the clipped values
+      skipped, _ = self.fused.reduce_and_apply(mean)
+      return skipped, gnorm
     # (2) reduce, last bucket first (its gradients were produced first)
     launched = {(s, b.index) for s, b, _ in self._pending}
     for s in self.group_keys:

@@ -23,7 +23,9 @@ class FusedDataParallel(object):
   def eligible(trainer, comm) -> bool:
     cfg = trainer.config
     return (trainer.device.type == "cuda" and not trainer.baseline and cfg.communication.fused_kernels
-            and 1 < comm.size <= 8 and trainer.max_grad_norm is None and cfg.offload.level == ""
+            and 1 < comm.size <= 8 and cfg.offload.level == ""
+            # clipping: only the reference's default clip-then-reduce (local norm, applied to the bucket before the kernel runs)
+            and (trainer.max_grad_norm is None or not cfg.communication.clip_after_allreduce)
             and cfg.zero.level in ("", "v0", "v1", "v2") and trainer.opt_kind in ("adam", "adamw")
             and cfg.optimizer.num_apply_group == 1
             and trainer.compute_dtype in (torch.bfloat16, torch.float16) and not isinstance(

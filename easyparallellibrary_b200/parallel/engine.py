@@ -5,7 +5,7 @@ pipeline (``epl/parallel/parallel.py:211-231``: offload -> micro-batch clone ->
 replica clone -> gradient aggregation -> schedule -> IO slicing -> output
 merging).  Nothing is cloned: replicas are other ranks, micro-batches are loop
 iterations, schedules are instruction lists, gradient aggregation is a set of
-flat buckets reduced over NVLink while backward is still running.
+flat buckets in NVLink symmetric memory, each reduced + applied + re-gathered by one kernel.
 
 Semantics kept from the reference:
 

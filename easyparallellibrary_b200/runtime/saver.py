@@ -116,29 +116,61 @@ class ShardingLoader(object):
     return loaded
 
 
+def _optimizer_state(trainer) -> Dict[str, torch.Tensor]:
+  opt: Dict[str, torch.Tensor] = {}
+  for s in trainer.group_keys:
+    for i, o in enumerate(trainer.optimizers[s]):
+      for k, v in o.state_dict().items():
+        if isinstance(v, torch.Tensor):
+          opt["g%d.b%d.%s" % (s, i, k)] = v
+        elif isinstance(v, (int, float)):
+          opt["g%d.b%d.%s" % (s, i, k)] = torch.tensor(v)
+  for s, z in getattr(trainer, "zero3", {}).items():
+    for i, sd in enumerate(z.state_dict()):
+      for k, v in sd.items():
+        if isinstance(v, torch.Tensor):
+          opt["z%d.u%d.%s" % (s, i, k)] = v
+        elif isinstance(v, (int, float)):
+          opt["z%d.u%d.%s" % (s, i, k)] = torch.tensor(v)
+  return opt
+
+
+def _optimizer_is_sharded(trainer) -> bool:
+  """ZeRO v0 / v1 / v2 and the fused data-parallel path keep a 1/N shard of the optimizer state per rank; ZeRO-3 additionally
+  shards the parameters.  Such state cannot be written by the first replica alone."""
+  return any(trainer._sharded.values()) or bool(getattr(trainer, "zero3", {}))
+
+
 def save_checkpoint(trainer, directory: str, bucket_bytes: int = BUCKET_BYTES) -> Optional[List[str]]:
-  """First replica of every pipeline stage writes its stage; with split taskgraphs every rank writes its shards."""
+  """Model weights: the first replica of every pipeline stage writes its stage (with split taskgraphs every rank writes its
+  shards).  Optimizer state: the first replica, or — when it is sharded over the data-parallel ranks (ZeRO, fused path) —
+  every rank writes its own shard under ``rank<r>/`` (the reference skips optimizer slots under ZeRO, ``hooks.py:340-344``,
+  so a resumed run silently restarts them; here they resume exactly)."""
   trainer.build()
+  per_rank_dirs = trainer.plan.num_stages > 1 or trainer.has_split
   must_write = trainer.is_first_replica or getattr(trainer, "has_split", False)
+  sharded = _optimizer_is_sharded(trainer)
   files = None
-  if must_write:
-    sub = os.path.join(directory, "rank%d" % _rank()) if (trainer.plan.num_stages > 1 or trainer.has_split) else directory
-    builder = MemoryEfficientBuilder(sub, bucket_bytes)
-    state = {}
-    for s in trainer.plan.local_stages:
-      for k, v in trainer.stage_modules[s].state_dict().items():
-        state["stage%d.%s" % (s, k)] = v
-    opt = {}
-    for s in trainer.group_keys:
-      for i, o in enumerate(trainer.optimizers[s]):
-        for k, v in o.state_dict().items():
-          if isinstance(v, torch.Tensor):
-            opt["g%d.b%d.%s" % (s, i, k)] = v
-          else:
-            opt["g%d.b%d.%s" % (s, i, k)] = torch.tensor(v) if isinstance(v, (int, float)) else v
-    files = builder.save(state, "model", {"global_step": trainer.global_step, "loss_scale": trainer.scaler.loss_scale})
-    if trainer.is_first_replica or trainer.has_split or any(trainer._sharded.values()):
-      builder.save(opt, "optim")
+  zero3 = getattr(trainer, "zero3", {})
+  for z in zero3.values():                      # ZeRO-3 keeps parameters released between steps: materialise them for the export
+    z.gather_all()
+  try:
+    if must_write:
+      sub = os.path.join(directory, "rank%d" % _rank()) if per_rank_dirs else directory
+      builder = MemoryEfficientBuilder(sub, bucket_bytes)
+      state = {}
+      for s in trainer.plan.local_stages:
+        for k, v in trainer.stage_modules[s].state_dict().items():
+          state["stage%d.%s" % (s, k)] = v
+      files = builder.save(state, "model", {"global_step": trainer.global_step, "loss_scale": trainer.scaler.loss_scale})
+      if not sharded:
+        builder.save(_optimizer_state(trainer), "optim")
+  finally:
+    for z in zero3.values():
+      z.release_all()
+  if sharded:
+    MemoryEfficientBuilder(os.path.join(directory, "rank%d" % _rank()), bucket_bytes).save(
+        _optimizer_state(trainer), "optim", {"global_step": trainer.global_step})
   import torch.distributed as dist
   if dist.is_initialized():
     dist.barrier()
@@ -148,8 +180,9 @@ def save_checkpoint(trainer, directory: str, bucket_bytes: int = BUCKET_BYTES) -
 def load_checkpoint(trainer, directory: str) -> int:
   """Restore on every rank from the files written by ``save_checkpoint``; returns the restored global step."""
   trainer.build()
-  sub = os.path.join(directory, "rank%d" % _rank())
-  if not os.path.isdir(sub):
+  mine = os.path.join(directory, "rank%d" % _rank())
+  sub = mine
+  if not os.path.exists(os.path.join(sub, "model.index.json")):
     # written by the first replica only: find the writer that holds the same stage
     sub = directory
     if trainer.plan.num_stages > 1:
@@ -157,21 +190,42 @@ def load_checkpoint(trainer, directory: str) -> int:
       sub = os.path.join(directory, "rank%d" % trainer.plan.stage_ranks[stage][0][0])
   builder = MemoryEfficientBuilder(sub)
   state, extra = builder.load("model")
-  for s in trainer.plan.local_stages:
-    prefix = "stage%d." % s
-    sd = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
-    own = trainer.stage_modules[s].state_dict()
-    for k, v in sd.items():
-      if k in own:
-        own[k].copy_(v.to(own[k].dtype))
-  if os.path.exists(os.path.join(sub, "optim.index.json")):
-    opt, _ = builder.load("optim")
+  zero3 = getattr(trainer, "zero3", {})
+  if not zero3:
+    for s in trainer.plan.local_stages:
+      prefix = "stage%d." % s
+      sd = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
+      own = trainer.stage_modules[s].state_dict()
+      for k, v in sd.items():
+        if k in own:
+          own[k].copy_(v.to(own[k].dtype))
+  # optimizer state: this rank's own shard if one was written, else the first replica's full state
+  opt_dir = mine if os.path.exists(os.path.join(mine, "optim.index.json")) else sub
+  restored = set()
+  if os.path.exists(os.path.join(opt_dir, "optim.index.json")):
+    opt, _ = MemoryEfficientBuilder(opt_dir).load("optim")
     for s in trainer.group_keys:
       for i, o in enumerate(trainer.optimizers[s]):
         pre = "g%d.b%d." % (s, i)
         if pre + "master" in opt and opt[pre + "master"].numel() == o.master.numel():
           o.load_state_dict({"step": int(opt[pre + "step"]), "master": opt[pre + "master"],
                              "m": opt.get(pre + "m"), "v": opt.get(pre + "v")})
+          restored.add((s, i))
+    for s, z in zero3.items():
+      sds = []
+      for i, u in enumerate(z.units):
+        pre = "z%d.u%d." % (s, i)
+        sds.append({k[len(pre):]: (int(v) if k.endswith(".step") else v) for k, v in opt.items() if k.startswith(pre)})
+      if all("shard_param" in sd for sd in sds):
+        z.load_state_dict(sds)
+  # optimizers without restored state restart from the restored weights (fp32 master = parameters)
+  for s in trainer.group_keys:
+    comm, flat = trainer.dp_comms[s], trainer.flats[s]
+    for i, (b, o) in enumerate(zip(flat.buckets, trainer.optimizers[s])):
+      if (s, i) not in restored:
+        sharded = trainer._sharded[s]
+        lo, hi = b.shard_range(comm.rank if sharded else 0, comm.size if sharded else 1)
+        o.master.copy_(b.flat_param[lo:hi].to(o.master.dtype))
   trainer.global_step = int(extra.get("global_step", 0))
   if hasattr(trainer.scaler, "loss_scale") and "loss_scale" in extra:
     trainer.scaler.loss_scale = extra["loss_scale"]

@@ -520,6 +520,8 @@ class Trainer(object):
       for comm in self.dp_comms.values():
         if comm.size > 1:
           comm.primary.all_reduce(bad, "max")
+      if self.plan.pipeline:                   # ... and by every stage: a step is skipped everywhere or nowhere
+        self.pipe.all_reduce_over_stages(bad)
       found_inf = bool(bad.item() > 0)
     if self.scaler.update(found_inf):
       return True, gnorm
@@ -636,6 +638,8 @@ class Trainer(object):
     if not self._built:
       self.build()
     batch = tuple(_to_device(x, self.device) for x in batch)
+    if self.compute_dtype is not None and batch and isinstance(batch[0], torch.Tensor) and batch[0].is_floating_point():
+      batch = (batch[0].to(self.compute_dtype),) + batch[1:]          # same input cast as step() (AMP)
     was = self.model.training
     self.model.eval()
     Graph.get().current_micro_batch = batch

@@ -407,3 +407,29 @@ def test_checkpoint_resume_with_sharded_optimizer_state(tmp_path, zero):
   for step, after, resumed in res:
     assert step == 2
     np.testing.assert_allclose(resumed, after, rtol=0, atol=1e-6)
+
+
+def _amp_pipeline_worker(rank, world):
+  import easyparallellibrary_b200 as epl
+  epl.init(epl.Config({"pipeline.num_micro_batch": 2, "amp.level": "O1", "amp.loss_scale": "dynamic"}))
+  torch.manual_seed(0)
+  with epl.replicate(1, name="s0"):
+    a = nn.Sequential(nn.Linear(10, 16), nn.ReLU())
+  with epl.replicate(1, name="s1"):
+    b = nn.Linear(16, 2)
+  tr = epl.Trainer(nn.Sequential(a, b), "sgd", lr=1000.0, loss_fn=lambda y, t: nn.functional.cross_entropy(y.float(), t))
+  g = torch.Generator().manual_seed(0)
+  skipped = []
+  for _ in range(6):
+    x, y = torch.randn(8, 10, generator=g) * 50, torch.randint(0, 2, (8,), generator=g)
+    skipped.append(bool(tr.step(x, y).skipped))
+  ev = tr.eval_step(torch.randn(4, 10), torch.randint(0, 2, (4,)))            # fp32 input is cast like in step()
+  return skipped, float(tr.scaler.loss_scale), ev is not None
+
+
+def test_amp_overflow_is_skipped_on_every_pipeline_stage():
+  """2-stage pipeline + fp16 dynamic loss scaling with a learning rate that overflows (reference amp_parallel_test.py /
+  test_amp_parallel.sh): an overflow seen by one stage skips the update on ALL stages and the loss scales stay equal."""
+  res = run_distributed(_amp_pipeline_worker, 2)
+  assert res[0][0] == res[1][0] and any(res[0][0]) and res[0][1] == res[1][1]
+  assert res[1][2] and not res[0][2]                                             # the loss lives on the last stage

@@ -433,3 +433,21 @@ def test_amp_overflow_is_skipped_on_every_pipeline_stage():
   res = run_distributed(_amp_pipeline_worker, 2)
   assert res[0][0] == res[1][0] and any(res[0][0]) and res[0][1] == res[1][1]
   assert res[1][2] and not res[0][2]                                             # the loss lives on the last stage
+
+
+@pytest.mark.parametrize("policy", ["PreferBackward", "PreferForward", "PreferBackwardOptimizer"])
+def test_four_stage_pipeline_matches_single_process(policy):
+  """Four stages x eight micro-batches: deeper than the 2-stage case, so middle stages both receive and send in each direction
+  and the receive hoisting of every schedule is exercised."""
+  conf = {"pipeline.num_micro_batch": 8, "pipeline.strategy": policy}
+  base = run_distributed(_train_pipe, 1, args=(conf, 4))[0]
+  res = run_distributed(_train_pipe, 4, args=(conf, 4), timeout=300)
+  assert all(r[2] for r in res)
+  merged = {}
+  for r in res:
+    merged.update(r[1])
+  assert set(merged) == set(base[1])
+  assert max(float(np.abs(merged[k] - base[1][k]).max()) for k in merged) < 1e-6
+  for r in res:
+    for a, b in zip(r[0], base[0]):
+      assert abs(a - b) < 1e-5

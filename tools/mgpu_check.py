@@ -206,6 +206,34 @@ def check_tp(dev, world, rank):
     json.dump({"%d_%d_%d_%s_%s" % k: v for k, v in results.items()}, open("gpurun_out/tp_fused_bench_w%d.json" % world, "w"))
 
 
+def check_tp_train(dev, world, rank):
+  """Tensor-parallel BERT layers trained for a few steps with the fused collective GEMMs (K3a / K3b forward AND their
+  backward pairing in ops/tp_fused.py) vs the NCCL + GEMM path: losses and weights must agree."""
+  from easyparallellibrary_b200.models.bert import Bert, BertConfig
+  from easyparallellibrary_b200.ops import tp_fused
+  res = {}
+  for fused in (False, True):
+    tp_fused.USE_FUSED = fused
+    epl.init(epl.Config({"amp.level": "bf16", "cluster.colocate_split_and_replicate": True}))
+    epl.set_default_strategy(epl.replicate(device_count=1))
+    torch.manual_seed(0)
+    model = Bert(BertConfig.named("tiny", hidden_size=256, num_attention_heads=4, intermediate_size=1024, tensor_parallel=world))
+    tr = epl.Trainer(model, "adamw", lr=1e-3, eps=1.0).build()          # eps=1: no sign amplification of rounding differences
+    g = torch.Generator().manual_seed(3)                                 # the whole TP group sees the same batch
+    losses = []
+    for _ in range(4):
+      ids = torch.randint(0, 1000, (8, 128), generator=g).to(dev)
+      s, e = torch.randint(0, 128, (8,), generator=g).to(dev), torch.randint(0, 128, (8,), generator=g).to(dev)
+      losses.append(float(tr.step(ids, s, e).loss))
+    torch.cuda.synchronize()
+    res[fused] = (losses, torch.cat([p.detach().float().flatten() for p in model.parameters()]))
+  tp_fused.USE_FUSED = True
+  dl = max(abs(a - b) for a, b in zip(res[True][0], res[False][0]))
+  dp = (res[True][1] - res[False][1]).abs().max().item()
+  log("TP training, fused vs NCCL+GEMM: losses %s vs %s (max diff %.2e), max |dparam| %.2e" % (res[True][0], res[False][0], dl, dp))
+  assert dl < 0.02 and dp < 8e-3
+
+
 def check_moe(dev, world, rank):
   """K5: the peer-store all-to-all (csrc/symm.cu alltoall_p2p_kernel) vs the NCCL all-to-all, values and timing; then the
   expert-parallel MoE layer forward/backward with either transport."""
@@ -269,6 +297,8 @@ def main():
     check_fused(dev, world, rank)
   if "tp" in what:
     check_tp(dev, world, rank)
+  if "tptrain" in what:
+    check_tp_train(dev, world, rank)
   if "moe" in what:
     check_moe(dev, world, rank)
   dist.barrier()

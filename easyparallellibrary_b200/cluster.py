@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import json
 import os
-from typing import Dict, Iterable, List, NamedTuple, Optional, Sequence, Union
+from typing import Iterable, List, NamedTuple, Optional, Sequence, Union
 
 from easyparallellibrary_b200.utils import constant
 

@@ -15,7 +15,7 @@ as symmetric memory for the in-kernel NVLink reduce-scatter.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import torch
 

@@ -9,7 +9,7 @@ autodiff or not at all (``reduce_scatter``, ``allgatherv``, ``alltoallv``,
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 

@@ -6,7 +6,7 @@ signal-pad slots) — the role TF collective group/instance keys play in the ref
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Sequence, Tuple
 
 

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import weakref
 from collections import OrderedDict
-from typing import Any, Dict, Iterable, List, Optional
+from typing import Any, Dict, List, Optional
 
 from easyparallellibrary_b200.ir.node import Node
 from easyparallellibrary_b200.ir.phase import ModelPhase

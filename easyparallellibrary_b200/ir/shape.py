@@ -4,7 +4,7 @@ and ``ops/tensor_parallel.add_weight`` use them to slice checkpoints."""
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 
 @dataclass(frozen=True)

@@ -14,7 +14,7 @@ recomputed by gradient checkpointing (``epl_collective``), like the reference (`
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional, Tuple
+from typing import Dict
 
 import torch
 from torch import nn

@@ -17,7 +17,6 @@ all-gather->GEMM is a GEMM->reduce-scatter and vice versa.
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 

@@ -10,12 +10,12 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
 from easyparallellibrary_b200.ops import _lib
-from easyparallellibrary_b200.runtime.symmetric import SignalPad, SymmetricBuffer, _sym_lib
+from easyparallellibrary_b200.runtime.symmetric import SignalPad, _sym_lib
 
 
 class FusedDataParallel(object):

@@ -116,6 +116,12 @@ def build_plan(graph: Optional[Graph] = None, cluster=None, config=None, rank: O
     plan.local_stages = list(range(len(plan.stage_taskgraphs)))
     plan.stage_of_rank = {r: list(plan.local_stages) for r in all_ranks}
     plan.pipeline = False       # all stages on every rank: micro-batches become gradient accumulation
+    if len(stage_tgs) > 1 and world > 1:
+      from easyparallellibrary_b200.utils.logging import get_logger
+      get_logger().warning(
+          "%d replicate taskgraphs are colocated on every GPU (cluster.colocate_split_and_replicate): they run back to back, "
+          "not as a pipeline; %s", len(stage_tgs),
+          "the %d micro-batches are gradient accumulation" % M if M > 1 else "set the flag to False for inter-layer placement")
     return plan
 
   counts = [t.num_device_per_replica for t in tgs]

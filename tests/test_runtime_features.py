@@ -302,3 +302,21 @@ def test_bench_reference_arm_reports_unavailable():
   assert r.returncode == 0
   line = json.loads(r.stdout.strip().splitlines()[-1])
   assert line["impl"] == "reference" and "unavailable" in line
+
+
+@pytest.mark.parametrize("nproc,argv", [
+    (2, ["train_gpt2.py", "--model", "tiny", "--batch", "2", "--seq", "32", "--steps", "2", "--stages", "2", "--micro", "2"]),
+    (2, ["train_bert_pipeline.py", "--size", "tiny", "--batch", "4", "--seq", "16", "--steps", "2", "--tp", "2"]),
+    (2, ["train_moe.py", "--batch", "2", "--seq", "16", "--steps", "2", "--experts", "4"]),
+])
+def test_examples_run_distributed_through_the_launcher(tmp_path, nproc, argv):
+  """Pipeline, tensor-parallel and expert-parallel examples as real multi-process jobs (gloo) started by ``epl-launch``."""
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  cmd = [sys.executable, "-m", "easyparallellibrary_b200.utils.launcher", "--num_workers", "1", "--gpu_per_worker", str(nproc),
+         "--backend", "gloo", "--log_dir", str(tmp_path), os.path.join(root, "examples", argv[0])] + argv[1:]
+  env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+  r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=400)
+  logs = "".join(open(os.path.join(tmp_path, f)).read()[-1500:] for f in sorted(os.listdir(tmp_path)))
+  assert r.returncode == 0 and "step 1 loss" in r.stdout, r.stdout[-1500:] + logs

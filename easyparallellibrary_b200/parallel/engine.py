@@ -370,6 +370,7 @@ class Trainer(object):
   # ================================================================== gradient hooks
   def _install_grad_hooks(self) -> None:
     self._bucket_of: Dict[int, Tuple[int, Bucket, int]] = {}
+    self._grad_view: Dict[int, Tuple[torch.Tensor, int]] = {}      # parameter -> (its view of the flat gradient, data_ptr)
     self._overlap = False
     self._first_micro_batch = True
     self._last_micro_batch = True
@@ -378,6 +379,8 @@ class Trainer(object):
       for b in flat.buckets:
         for p, o in zip(b.params, b.offsets):
           self._bucket_of[id(p)] = (s, b, o)
+          view = b.flat_grad[o:o + p.numel()].view(p.shape)      # the buckets are persistent: build the view once, not per hook call
+          self._grad_view[id(p)] = (view, view.data_ptr())
           p.register_post_accumulate_grad_hook(self._on_grad_ready)
           if p.is_cuda and b.flat_grad.dtype == p.dtype:
             # weight-gradient GEMMs accumulate straight into the flat bucket (ops/linear.py:_sink_weight_grad)
@@ -387,10 +390,11 @@ class Trainer(object):
 
   def _on_grad_ready(self, p: nn.Parameter) -> None:
     s, b, o = self._bucket_of[id(p)]
-    if p.grad is not None:
-      view = b.flat_grad[o:o + p.numel()].view(p.shape)
-      if p.grad.data_ptr() != view.data_ptr():       # autograd replaced the view: fold it back
-        view.add_(p.grad)
+    g = p.grad
+    if g is not None:
+      view, ptr = self._grad_view[id(p)]
+      if g.data_ptr() != ptr:                        # autograd replaced the view: fold it back
+        view.add_(g)
         p.grad = view if view.dtype == p.dtype else None
     b.ready += 1
     if self._last_micro_batch and b.ready % len(b.params) == 0:

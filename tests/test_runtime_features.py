@@ -320,3 +320,13 @@ def test_examples_run_distributed_through_the_launcher(tmp_path, nproc, argv):
   r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=400)
   logs = "".join(open(os.path.join(tmp_path, f)).read()[-1500:] for f in sorted(os.listdir(tmp_path)))
   assert r.returncode == 0 and "step 1 loss" in r.stdout, r.stdout[-1500:] + logs
+
+
+def test_common_helpers():
+  from easyparallellibrary_b200.utils import common
+  assert common.strip_stage_prefix(common.add_stage_prefix("h.0.weight", 3)) == (3, "h.0.weight")
+  assert common.strip_stage_prefix("embed.wte.weight") == (None, "embed.wte.weight")
+  assert common.parse_device_string(common.device_string(2, 5)) == (2, "GPU", 5)
+  with pytest.raises(ValueError):
+    common.parse_device_string("cuda:0")
+  assert common.gcd_many([4, 6, 10]) == 2 and common.lcm_many([2, 3, 4]) == 12

@@ -53,3 +53,55 @@ class ThroughputMeter(object):
     per_step = ms / self._timed
     return {"ms_per_step": per_step, "per_second": self.items_per_step * world_items_multiplier / (per_step / 1e3),
             "steps": self._timed, "unit": self.unit}
+
+
+class PhaseTimer(object):
+  """Time one method of an object on the device (CUDA events on the current stream) or on the host (CPU runs).
+
+  ``bench.py`` wraps ``Trainer._reduce_and_apply`` with it to report the *exposed* gradient-reduction + optimizer time per step
+  (the fused bucket kernels run after backward on the main stream, so their event span is exactly what the step pays) next to
+  that phase's roofline — the "exposed comm ms/step; fused-path % of roofline" part of the headline metric."""
+
+  def __init__(self, obj, method: str, use_cuda: bool):
+    self.obj, self.method, self.use_cuda = obj, method, bool(use_cuda)
+    self.orig = getattr(obj, method)
+    self.spans = []
+    setattr(obj, method, self._call)
+
+  def _call(self, *args, **kwargs):
+    if self.use_cuda:
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      out = self.orig(*args, **kwargs)
+      e1.record()
+      self.spans.append((e0, e1))
+    else:
+      t0 = time.perf_counter()
+      out = self.orig(*args, **kwargs)
+      self.spans.append(time.perf_counter() - t0)
+    return out
+
+  def reset(self) -> None:
+    self.spans = []
+
+  def total_ms(self) -> float:
+    if self.use_cuda:
+      torch.cuda.synchronize()
+      return float(sum(a.elapsed_time(b) for a, b in self.spans))
+    return float(sum(self.spans) * 1e3)
+
+  def restore(self) -> None:
+    setattr(self.obj, self.method, self.orig)
+
+
+def fused_dp_roofline_ms(num_params: int, world: int, hbm_gbs: float = 6400.0, nvlink_gbs: float = 900.0, grad_bytes: int = 2) -> float:
+  """Lower bound of reduce-scatter + AdamW + all-gather for ``num_params`` parameters over ``world`` NVLink peers:
+  every rank pulls the (W-1)/W remote part of its shard's partial gradients, streams 24 B/param of fp32 optimizer state for its
+  1/W shard (read + write of master, m, v), and pushes its new 16-bit weights to W-1 peers.  With one GPU it is the local
+  AdamW stream (30 B/param)."""
+  if world <= 1:
+    return num_params * 30.0 / (hbm_gbs * 1e9) * 1e3
+  remote = (world - 1) / world * num_params * grad_bytes
+  link = 2.0 * remote / (nvlink_gbs * 1e9)
+  adam = (num_params / world) * 24.0 / (hbm_gbs * 1e9)
+  return (link + adam) * 1e3

@@ -52,6 +52,28 @@ def init(config=None, init_process_group: bool = True):
   return env
 
 
+def shutdown() -> None:
+  """Leave the job cleanly: wait for every rank, then destroy the process group.  Without it the rank that hosts the rendezvous
+  store can exit while its peers are still tearing down and they die with a non-zero exit code (seen as a flaky launcher
+  test); call it at the end of a training script."""
+  try:
+    import gc
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+      dist.barrier()
+      # drop every cached communicator / process-group handle first: a ProcessGroup object that is still referenced from a
+      # module-level cache is destroyed during interpreter finalisation, after the store it depends on, and gloo then calls
+      # std::terminate ("terminate called without an active exception")
+      from easyparallellibrary_b200.communicators import backend, collective_communicator
+      collective_communicator._REGISTRY.clear()
+      backend.reset_groups()
+      Env.get().reset()
+      gc.collect()
+      dist.destroy_process_group()
+  except Exception:
+    pass
+
+
 def set_default_strategy(strategy):
   """Everything created outside an explicit scope belongs to ``strategy``
   (replicate only).  Calling it again opens the next taskgraph — the idiom the

@@ -38,3 +38,4 @@ for step in range(args.steps):
   out = trainer.step(ids, start, end)
   if int(os.environ.get("RANK", 0)) == 0:
     print("step %d loss %s" % (step, out.loss), flush=True)
+epl.shutdown()

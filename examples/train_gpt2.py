@@ -41,3 +41,4 @@ for step in range(args.steps):
   out = trainer.step(tokens, tokens)
   if rank == 0:
     print("step %d loss %.4f" % (step, out.item()), flush=True)
+epl.shutdown()

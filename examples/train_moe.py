@@ -29,3 +29,4 @@ for step in range(args.steps):
   out = trainer.step(tok, tok)
   if int(os.environ.get("RANK", 0)) == 0:
     print("step %d loss %.4f" % (step, out.item()), flush=True)
+epl.shutdown()

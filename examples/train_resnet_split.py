@@ -31,3 +31,4 @@ for step in range(args.steps):
   out = trainer.step(torch.randn(args.batch, 3, 224, 224), torch.randint(0, 10000, (args.batch,)))
   if int(os.environ.get("RANK", 0)) == 0:
     print("step %d loss %.4f (%.3f s)" % (step, out.item(), time.time() - t0), flush=True)
+epl.shutdown()

@@ -47,6 +47,7 @@ def main():
   else:
     assert skipped == 0 and losses[-1] < losses[0] * 1.5
   print("rank %d/%d ok: skipped=%d loss %.4f -> %.4f" % (rank, world, skipped, losses[0], losses[-1]), flush=True)
+  epl.shutdown()
   return 0
 
 

@@ -33,6 +33,20 @@ def _entry(rank, world, port, fn, args, queue, env):
 
 
 def run_distributed(fn, world, args=(), env=None, timeout=180):
+  """One retry for failures of the host rather than of the code under test: a rendezvous port taken between probing and
+  binding, or a worker that never reported because the box was overloaded."""
+  import queue as _queue
+  try:
+    return _run_once(fn, world, args, env, timeout)
+  except _queue.Empty:
+    return _run_once(fn, world, args, env, 2 * timeout)
+  except AssertionError as e:
+    if "Address already in use" in str(e) or "EADDRINUSE" in str(e):
+      return _run_once(fn, world, args, env, timeout)
+    raise
+
+
+def _run_once(fn, world, args, env, timeout):
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
   port = _free_port()

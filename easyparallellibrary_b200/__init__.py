@@ -65,6 +65,12 @@ def shutdown() -> None:
       # module-level cache is destroyed during interpreter finalisation, after the store it depends on, and gloo then calls
       # std::terminate ("terminate called without an active exception")
       from easyparallellibrary_b200.communicators import backend, collective_communicator
+      try:                                   # in-tree NCCL communicators (GPU jobs): synchronise and destroy them explicitly
+        from easyparallellibrary_b200.communicators import native as _native
+        for be in list(getattr(_native, "_LIVE", [])):
+          be.close()
+      except Exception:
+        pass
       collective_communicator._REGISTRY.clear()
       backend.reset_groups()
       Env.get().reset()

@@ -43,6 +43,15 @@ def init(config=None, init_process_group: bool = True):
     # any kernel wait for them (deadlock under 1F1B, see parallel/pipeline.py).  Takes effect if the CUDA context does not
     # exist yet; the executor additionally runs a communication-free warm-up pass of every stage.
     os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+  if env.config.cluster.run_visible_devices:
+    # reference cluster.run_visible_devices: "visible devices for the session" (epl/config.py:160-164).  One process per GPU here:
+    # the list restricts which physical GPUs this job's processes may use; it must be exported before the CUDA context exists
+    import torch
+    if torch.cuda.is_available() and torch.cuda.is_initialized():
+      from easyparallellibrary_b200.utils.logging import get_logger
+      get_logger().warning("cluster.run_visible_devices=%s ignored: the CUDA context already exists", env.config.cluster.run_visible_devices)
+    else:
+      os.environ["CUDA_VISIBLE_DEVICES"] = str(env.config.cluster.run_visible_devices)
   if init_process_group and int(os.environ.get("WORLD_SIZE", "1")) > 1:
     from easyparallellibrary_b200.runtime.dist import ensure_process_group
     ensure_process_group()

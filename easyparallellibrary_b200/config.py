@@ -39,6 +39,9 @@ _opt("communication", "clip_after_allreduce", False, "Clip gradients after the r
 _opt("communication", "gradients_reduce_method", constant.REDUCE_MEAN, "mean or sum over replicas and micro-batches.")
 _opt("communication", "fused_kernels", True,
      "B200 extension: use in-kernel NVLink (P2P / multimem) fused collectives where available.")
+_opt("communication", "fused_splits", 16,
+     "B200 extension: number of gradient buckets when the fused reduce-scatter+AdamW+all-gather kernel runs (more, smaller "
+     "buckets overlap better with backward; only the last one is exposed).")
 _opt("pipeline", "num_stages", -1, "Number of stages for automatic partitioning.")
 _opt("pipeline", "num_micro_batch", 1, "Micro-batches per step (pipeline depth or accumulation count).")
 _opt("pipeline", "strategy", constant.DEFAULT_PIPELINE_STRATEGY,

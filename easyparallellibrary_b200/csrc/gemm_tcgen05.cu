@@ -18,12 +18,12 @@
 // B stored [K,N] — what the backward GEMMs dX = dY @ W and dW = dY^T @ X need), selected per
 // operand through the UMMA instruction descriptor + shared-memory descriptor.
 //
-// Three kernels share this file:
+// Two kernels share this file:
 //   gemm_tcgen05_kernel<BN, comm>  1-CTA tiles (described above); also the compute half of the fused collective modes
 //                                  COMM_AG (all-gather -> GEMM), COMM_RS (GEMM -> reduce-scatter), COMM_AGB (weight gather);
 //   gemm2_tcgen05_kernel           the default for M, N >= 256: CTA pairs (cta_group::2), 256 x {256,192,128} tiles,
-//                                  6-stage ring, 8 epilogue warps, aux-operand prefetch, red.add accumulation;
-//   gemm4_tcgen05_kernel           opt-in: 4-CTA clusters, two pairs sharing one multicast B tile.
+//                                  6-stage ring, 8 epilogue warps, aux-operand prefetch, red.add accumulation, dynamic
+//                                  (atomic-counter) tile scheduler, narrow MMA on the ragged last column tile.
 //
 // The reference has no GEMM of its own (all math is stock TF/cuBLAS).
 #include "epl_common.cuh"
@@ -54,6 +54,7 @@ struct GemmParams {
   int ab_format;           // 1 = bf16, 0 = fp16
   float alpha;
   int bn2;                 // 2-CTA kernel: tile width (128 / 192 / 256), chosen per shape by pick_bn2()
+  uint32_t* sched_counter; // 2-CTA kernel: global tile counter of the dynamic scheduler (one per stream, self-resetting)
 };
 
 // Fused collective (tensor-parallel) state.  mode 1: all-gather -> GEMM, mode 2: GEMM -> reduce-scatter.
@@ -758,88 +759,143 @@ EPL_DEVICE void epilogue_chunk32(const GemmParams& p, int row, int col0, const u
   }
 }
 
-// Epilogue of the cta_group::2 kernels: each CTA drains its 128 rows x BN columns with 8 warps (two per TMEM lane quarter).
-// `pairs` CTA pairs are stacked along M inside one cluster (1 for the 2-CTA kernel, 2 for the 4-CTA multicast kernel);
-// `pair` is this CTA's pair.
-EPL_DEVICE void gemm2_epilogue(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int cta,
-                               int warp, int lane, int cluster_id, int num_clusters, int m_blocks, int n_blocks, int pairs, int pair) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Dynamic tile scheduler of the 2-CTA kernel.  Tiles are not pre-assigned (tile = cluster_id + i * num_clusters): the
+// leader CTA's producer thread draws the next tile index from a global counter (atomicAdd) and publishes it through a
+// 4-deep shared-memory ring to every role of BOTH CTAs of the pair (its own MMA / epilogue warps through local shared
+// memory, the peer CTA's producer / epilogue warps through distributed shared memory + a remote mbarrier arrive).
+// Why: (1) a concurrently running collective kernel (the fused gradient reduce-scatter + AdamW + all-gather of
+// csrc/symm.cu, launched per bucket while backward is still running) holds a few SMs; with static assignment the CTA
+// pairs that cannot be scheduled start late and then still walk their whole tile list (measured: 122.8 vs 117.7 ms/step),
+// with a counter the running pairs simply absorb the work; (2) ragged last-column tiles are cheaper (narrow MMA, see
+// below) and a counter balances uneven tiles for free.
+// The counter resets itself: a launch performs exactly num_tiles + num_clusters draws (every pair ends on one terminal
+// draw), so the pair that receives the value num_tiles + num_clusters - 1 knows it is the last and stores 0.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSched = 4;
+
+EPL_DEVICE uint32_t mapa_u32(uint32_t cta_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(cta_rank));
+  return r;
+}
+EPL_DEVICE void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(cluster_addr), "r"(v) : "memory");
+}
+EPL_DEVICE void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+EPL_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+
+struct TileRing {
+  uint64_t* full;        // [kSched] per CTA: the slot holds a tile index
+  uint64_t* empty;       // [kSched] leader CTA only: every consumer of both CTAs has read the slot
+  volatile int* tile;    // [kSched] per CTA
+};
+
+// consumer side (every role except the leader's producer): next tile index, slot handed back to the leader
+EPL_DEVICE int ring_next(const TileRing& r, uint32_t& it, bool whole_warp, int lane) {
+  const uint32_t slot = it & (kSched - 1), par = (it / kSched) & 1;
+  mbar_wait_cluster(&r.full[slot], par);
+  const int t = r.tile[slot];
+  if (whole_warp) __syncwarp();
+  if (!whole_warp || lane == 0) mbar_arrive_cluster_release(mapa_u32(smem_u32(&r.empty[slot]), 0));
+  ++it;
+  return t;
+}
+
+// width of the MMA for the n-block at column n0: the ragged last column tile multiplies only the columns that exist
+// (rounded up to 32 so that each CTA of the pair holds a multiple of 16) instead of a full BN-wide tile
+EPL_DEVICE int tile_n_eff(int N, int n0, int BN) { return min(BN, (N - n0 + 31) & ~31); }
+
+// Epilogue of the cta_group::2 kernel: each CTA drains its 128 rows x BN columns with 8 warps (two per TMEM lane quarter).
+EPL_DEVICE void gemm2_epilogue(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, const TileRing& ring,
+                               int cta, int warp, int lane, int m_blocks, int n_blocks) {
   constexpr int BM2 = 256, kMaxBN = 256;
   const int BN = p.bn2;
   const int num_tiles = m_blocks * n_blocks;
-    // ================================ epilogue (both CTAs, 128 rows each; 8 warps) ================================
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const bool need_aux = p.epilogue == EPI_DGELU || p.epilogue == EPI_BIAS_RESIDUAL;
-    const bool rows_aligned = (p.ldd & 7) == 0;
-    const int half_cols = BN / 2;                                // 64 / 96 / 128 columns per epilogue warp
-    const int nchunks = half_cols / 32;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      int mb, nb;
-      tile_coords(tile, m_blocks, n_blocks, mb, nb);
-      const int row = (mb * pairs + pair) * BM2 + cta * BLOCK_M + quarter * 32 + lane;
-      const int n0 = nb * BN + half * half_cols;                 // this warp's columns
-      const bool fast = rows_aligned && n0 + half_cols <= p.N;
-      const bool row_ok = row < p.M;
-      const bool pf = need_aux && fast && row_ok;
-      const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + n0;
-      // aux for the first 64 columns is requested before the accumulator wait: its latency hides behind the main loop
-      uint4 ax0[8], ax1[8];
+  const int quarter = warp & 3, half = (warp - 2) >> 2;
+  const bool need_aux = p.epilogue == EPI_DGELU || p.epilogue == EPI_BIAS_RESIDUAL;
+  const bool rows_aligned = (p.ldd & 7) == 0;
+  const int half_cols = BN / 2;                                // 64 / 96 / 128 columns per epilogue warp
+  const int nchunks = half_cols / 32;
+  int acc = 0; uint32_t acc_phase = 0;
+  uint32_t it = 0;
+  for (;;) {
+    const int tile = ring_next(ring, it, true, lane);
+    if (tile >= num_tiles) break;
+    int mb, nb;
+    tile_coords(tile, m_blocks, n_blocks, mb, nb);
+    const int row = mb * BM2 + cta * BLOCK_M + quarter * 32 + lane;
+    const int n0 = nb * BN + half * half_cols;                 // this warp's columns
+    const bool row_ok = row < p.M;
+    const bool pf = need_aux && rows_aligned && row_ok;
+    const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldd + n0;
+    // aux for the first 64 columns is requested before the accumulator wait: its latency hides behind the main loop
+    uint4 ax0[8], ax1[8];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) ax0[g] = pf ? ld_nc_v4(arow + g * 8) : make_uint4(0, 0, 0, 0);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN + half * half_cols;
-      uint32_t r0[32], r1[32];
-      // ---- columns [0, 64) ----
-      tmem_ld_32x32(taddr, r0);
-      tmem_ld_32x32(taddr + 32, r1);
+    for (int g = 0; g < 8; ++g) ax0[g] = (pf && n0 + g * 8 + 8 <= p.N) ? ld_nc_v4(arow + g * 8) : make_uint4(0, 0, 0, 0);
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN + half * half_cols;
+    uint32_t r0[32], r1[32];
+    // ---- columns [0, 64) ----
+    tmem_ld_32x32(taddr, r0);
+    tmem_ld_32x32(taddr + 32, r1);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) ax1[g] = (pf && 64 + g * 8 < half_cols) ? ld_nc_v4(arow + 64 + g * 8) : make_uint4(0, 0, 0, 0);
-      tmem_ld_wait();
-      if (nchunks == 2) {                                        // accumulator stage drained into registers: hand it back early
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-      }
-      if (row_ok) {
-        const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[0]);
-        const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[4]);
-        if (fast) { epilogue_chunk32<true>(p, row, n0, r0, a0); epilogue_chunk32<true>(p, row, n0 + 32, r1, a1); }
-        else {
-          if (n0 < p.N) epilogue_chunk32<false>(p, row, n0, r0, a0);
-          if (n0 + 32 < p.N) epilogue_chunk32<false>(p, row, n0 + 32, r1, a1);
-        }
-      }
-      if (nchunks > 2) {
-        // ---- columns [64, 96) or [64, 128) ----
-        tmem_ld_32x32(taddr + 64, r0);
-        if (nchunks > 3) tmem_ld_32x32(taddr + 96, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        if (row_ok) {
-          const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[0]);
-          const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[4]);
-          if (fast) {
-            epilogue_chunk32<true>(p, row, n0 + 64, r0, a0);
-            if (nchunks > 3) epilogue_chunk32<true>(p, row, n0 + 96, r1, a1);
-          } else {
-            if (n0 + 64 < p.N) epilogue_chunk32<false>(p, row, n0 + 64, r0, a0);
-            if (nchunks > 3 && n0 + 96 < p.N) epilogue_chunk32<false>(p, row, n0 + 96, r1, a1);
-          }
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    for (int g = 0; g < 8; ++g)
+      ax1[g] = (pf && 64 + g * 8 < half_cols && n0 + 64 + g * 8 + 8 <= p.N) ? ld_nc_v4(arow + 64 + g * 8) : make_uint4(0, 0, 0, 0);
+    tmem_ld_wait();
+    if (nchunks == 2) {                                        // accumulator stage drained into registers: hand it back early
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
     }
+    if (row_ok) {
+      const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[0]);
+      const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax0[4]);
+      if (rows_aligned && n0 + 32 <= p.N) epilogue_chunk32<true>(p, row, n0, r0, a0);
+      else if (n0 < p.N) epilogue_chunk32<false>(p, row, n0, r0, a0);
+      if (rows_aligned && n0 + 64 <= p.N) epilogue_chunk32<true>(p, row, n0 + 32, r1, a1);
+      else if (n0 + 32 < p.N) epilogue_chunk32<false>(p, row, n0 + 32, r1, a1);
+    }
+    if (nchunks > 2) {
+      // ---- columns [64, 96) or [64, 128) ----
+      tmem_ld_32x32(taddr + 64, r0);
+      if (nchunks > 3) tmem_ld_32x32(taddr + 96, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (row_ok) {
+        const uint4 (&a0)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[0]);
+        const uint4 (&a1)[4] = *reinterpret_cast<const uint4 (*)[4]>(&ax1[4]);
+        if (rows_aligned && n0 + 96 <= p.N) epilogue_chunk32<true>(p, row, n0 + 64, r0, a0);
+        else if (n0 + 64 < p.N) epilogue_chunk32<false>(p, row, n0 + 64, r0, a0);
+        if (nchunks > 3) {
+          if (rows_aligned && n0 + 128 <= p.N) epilogue_chunk32<true>(p, row, n0 + 96, r1, a1);
+          else if (n0 + 96 < p.N) epilogue_chunk32<false>(p, row, n0 + 96, r1, a1);
+        }
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const GemmParams p) {
   // The tile is 256 rows (128 per CTA) x BN columns; BN is a runtime value (128 / 192 / 256) so one kernel serves every
-  // width pick_bn2() selects against wave quantisation.  Shared-memory stages and TMEM accumulator stages keep the
-  // 256-wide stride.
+  // width pick_bn2() selects.  Shared-memory stages and TMEM accumulator stages keep the 256-wide stride.
   constexpr int BM2 = 256, kMaxBN = 256;
   constexpr int kABytes = BLOCK_M * BLOCK_K * 2, kBBytes = (kMaxBN / 2) * BLOCK_K * 2, kStageBytes = kABytes + kBBytes;
   const int BN = p.bn2;
@@ -852,7 +908,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint64_t* empty_bar = full_bar + kStages2;
   uint64_t* tmem_full = empty_bar + kStages2;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  TileRing ring;
+  ring.full = tmem_empty + 2;
+  ring.empty = ring.full + kSched;
+  ring.tile = reinterpret_cast<volatile int*>(ring.empty + kSched);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(ring.tile) + kSched);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();
@@ -861,13 +921,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int n_blocks = (p.N + BN - 1) / BN;
   const int num_tiles = m_blocks * n_blocks;
   const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }   // 8 epilogue warps x 2 CTAs
+    // ring: 1 publisher; consumers = peer producer + MMA thread + 16 epilogue warps
+    for (int s = 0; s < kSched; ++s) { mbar_init(&ring.full[s], 1); mbar_init(&ring.empty[s], 18); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc2<kTmemCols>(tmem_slot);
@@ -877,13 +939,34 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================ TMA producer (both CTAs) ================================
+    // ================================ TMA producer (both CTAs); the leader's is also the tile scheduler ==============
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      uint32_t it = 0;
+      int tile = leader ? (int)atomicAdd(p.sched_counter, 1u) : 0;
+      for (;;) {
+        int next = 0;
+        if (leader) {
+          const uint32_t slot = it & (kSched - 1), par = (it / kSched) & 1;
+          mbar_wait_cluster(&ring.empty[slot], par ^ 1);
+          ring.tile[slot] = tile;
+          st_cluster_u32(mapa_u32(smem_u32(const_cast<int*>(&ring.tile[slot])), 1), (uint32_t)tile);
+          mbar_arrive(&ring.full[slot]);
+          mbar_arrive_cluster_release(mapa_u32(smem_u32(&ring.full[slot]), 1));
+          ++it;
+          if (tile >= num_tiles) {
+            if (tile == num_tiles + num_clusters - 1) *reinterpret_cast<volatile uint32_t*>(p.sched_counter) = 0u;   // last draw of the launch
+            break;
+          }
+          next = (int)atomicAdd(p.sched_counter, 1u);          // in flight while this tile's loads are issued
+        } else {
+          tile = ring_next(ring, it, false, 0);
+          if (tile >= num_tiles) break;
+        }
         int mb, nb;
         tile_coords(tile, m_blocks, n_blocks, mb, nb);
-        const int m0 = mb * BM2 + (int)cta * BLOCK_M, n0 = nb * BN + (int)cta * (BN / 2);
+        const int n_eff = tile_n_eff(p.N, nb * BN, BN);
+        const int m0 = mb * BM2 + (int)cta * BLOCK_M, n0 = nb * BN + (int)cta * (n_eff / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * kStageBytes;
@@ -903,17 +986,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
+        tile = next;
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ================================
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_f16(BM2, BN, p.ab_format, p.a_mn_major, p.b_mn_major);
       const uint32_t a_lbo = p.a_mn_major ? BLOCK_K * 128 : 16, b_lbo = p.b_mn_major ? BLOCK_K * 128 : 16;
       const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2, b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      uint32_t it = 0;
+      for (;;) {
+        const int tile = ring_next(ring, it, false, 0);
+        if (tile >= num_tiles) break;
+        int mb, nb;
+        tile_coords(tile, m_blocks, n_blocks, mb, nb);
+        const uint32_t idesc = make_idesc_f16(BM2, tile_n_eff(p.N, nb * BN, BN), p.ab_format, p.a_mn_major, p.b_mn_major);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kMaxBN;
@@ -936,7 +1025,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
   } else {
-    gemm2_epilogue(p, tmem_base, tmem_full, tmem_empty, (int)cta, warp, lane, cluster_id, num_clusters, m_blocks, n_blocks, 1, 0);
+    gemm2_epilogue(p, tmem_base, tmem_full, tmem_empty, ring, (int)cta, warp, lane, m_blocks, n_blocks);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -946,199 +1035,35 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// 4-CTA cluster = two cta_group::2 pairs stacked along M (a 512 x 256 super-tile) that SHARE the B tile: each CTA fetches a
-// quarter of B and multicasts it to the CTA with the same rank-in-pair of the other pair, so one k-block costs
-// 16 KB (A) + 8 KB (B) of L2 reads per CTA instead of 32 KB.  The 2-CTA kernel is L2-bandwidth bound on B200
-// (5770 of ~6300 B/clk chip-wide at 1.41 PFLOP/s, profiles/r1_gemm_bench_v3_widths.txt), so bytes per flop is the lever.
-//   * every TMA load (unicast A, multicast B) is the cta_group::2 flavour: its bytes are reported to the pair leader of the
-//     destination CTA, so each leader waits on one barrier for the 64 KB of its pair (a first version forwarded the
-//     non-leader's barrier with a remote arrive per stage and ran at 40 % of the 2-CTA kernel);
-//   * a stage is reusable when BOTH pairs' MMAs have consumed it (the sibling pair's multicast writes into it), so every
-//     MMA commit arrives on the empty barrier of all four CTAs (count 2).
-// ---------------------------------------------------------------------------------------------------------------------
-EPL_DEVICE void tma_load_2d_mcast(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-      :: "r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
-}
-// same, cta_group::2 flavour: in every destination CTA the completion bytes are reported to the barrier at this offset in
-// that CTA's pair LEADER (peer bit cleared), so the leader's MMA thread waits on one barrier for both halves of its pair
-EPL_DEVICE void tma_load_2d_2cta_mcast(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-      :: "r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1) : "memory");
-}
-EPL_DEVICE void umma_commit_mask(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               :: "r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-EPL_DEVICE void mbar_arrive_leader_release(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-EPL_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+// One draw counter per stream (launches on one stream are serialised, and the counter is back at zero when a launch ends).
+constexpr int kSchedSlots = 64;
+static uint32_t* sched_pool() {
+  static uint32_t* pool = nullptr;
+  if (pool == nullptr) {
+    if (cudaMalloc(&pool, kSchedSlots * 128) != cudaSuccess) { pool = nullptr; return nullptr; }
+    cudaMemset(pool, 0, kSchedSlots * 128);
   }
+  return pool;
+}
+static uint32_t* sched_counter_for(cudaStream_t st) {
+  static cudaStream_t owner[kSchedSlots];
+  static int used = 0;
+  uint32_t* pool = sched_pool();
+  if (pool == nullptr) return nullptr;
+  for (int i = 0; i < used; ++i) if (owner[i] == st) return pool + i * 32;
+  if (used == kSchedSlots) used = 1;                 // recycle (slot 0 stays with the first stream seen)
+  owner[used] = st;
+  return pool + (used++) * 32;
 }
 
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kGemm2Threads, 1)
-gemm4_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const GemmParams p) {
-  constexpr int BM2 = 256, BN = 256, kPairs = 2;
-  constexpr int kABytes = BLOCK_M * BLOCK_K * 2, kBBytes = (BN / 2) * BLOCK_K * 2, kStageBytes = kABytes + kBBytes;
-  constexpr int kTmemCols = 512;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes);
-  uint64_t* peer_full = full_bar + kStages2;          // leader only: the non-leader's stage is full
-  uint64_t* empty_bar = peer_full + kStages2;
-  uint64_t* tmem_full = empty_bar + kStages2;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cta = (int)(rank & 1), pair = (int)(rank >> 1);
-  const bool leader = cta == 0;
-  const int m_blocks = (p.M + BM2 * kPairs - 1) / (BM2 * kPairs);     // super-rows of 512
-  const int n_blocks = (p.N + BN - 1) / BN;
-  const int num_tiles = m_blocks * n_blocks;
-  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int cluster_id = blockIdx.x >> 2, num_clusters = gridDim.x >> 2;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
-    for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&peer_full[s], 1); mbar_init(&empty_bar[s], kPairs); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }   // 8 epilogue warps x 2 CTAs
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc2<kTmemCols>(tmem_slot);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ================================ TMA producer (every CTA) ================================
-    if (lane == 0) {
-      const uint16_t mask = (uint16_t)((1u << cta) | (1u << (cta + 2)));       // same rank-in-pair, both pairs
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        int mb, nb;
-        tile_coords(tile, m_blocks, n_blocks, mb, nb);
-        const int m0 = (mb * kPairs + pair) * BM2 + cta * BLOCK_M;
-        const int n0 = nb * BN + cta * (BN / 2);                               // this CTA's half of B (shared with the sibling pair)
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
-          unsigned char* sa = smem + stage * kStageBytes;
-          unsigned char* sb = sa + kABytes;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);       // both CTAs of the pair: A + two quarters of B each
-          const int k0 = kb * BLOCK_K;
-          if (!p.a_mn_major) {
-            tma_load_2d_2cta(sa, &map_a, &full_bar[stage], k0, m0);
-          } else {
-#pragma unroll
-            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d_2cta(sa + a * (BLOCK_K * 128), &map_a, &full_bar[stage], m0 + a * 64, k0);
-          }
-          // quarter `pair` of the B tile: 64 of the 128 rows (K-major) / one 64-column swizzle atom (MN-major) = 8 KB
-          if (!p.b_mn_major) tma_load_2d_2cta_mcast(sb + pair * (64 * 128), &map_b, &full_bar[stage], k0, n0 + pair * 64, mask);
-          else tma_load_2d_2cta_mcast(sb + pair * (BLOCK_K * 128), &map_b, &full_bar[stage], n0 + pair * 64, k0, mask);
-          if (++stage == kStages2) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      if (leader) {
-        // ================================ MMA issuer (leader CTA of each pair) ================================
-        const uint32_t idesc = make_idesc_f16(BM2, BN, p.ab_format, p.a_mn_major, p.b_mn_major);
-        const uint32_t a_lbo = p.a_mn_major ? BLOCK_K * 128 : 16, b_lbo = p.b_mn_major ? BLOCK_K * 128 : 16;
-        const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2, b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
-        const uint16_t pair_mask = (uint16_t)(3u << (2 * pair)), all_mask = 0xF;
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * BN;
-          for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-            const uint32_t sb = sa + kABytes;
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-              const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-              umma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0);
-            }
-            umma_commit_mask(&empty_bar[stage], all_mask);
-            if (kb == k_blocks - 1) umma_commit_mask(&tmem_full[acc], pair_mask);
-            if (++stage == kStages2) { stage = 0; phase ^= 1; }
-          }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-      }
-    }
-  } else {
-    GemmParams q = p;
-    q.bn2 = BN;
-    gemm2_epilogue(q, tmem_base, tmem_full, tmem_empty, cta, warp, lane, cluster_id, num_clusters, m_blocks, n_blocks, kPairs, pair);
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc2<kTmemCols>(tmem_base);
-  }
+// after an aborted launch (sticky error, killed kernel) the counters may be non-zero: tests / error paths call this
+extern "C" int epl_gemm_reset_scheduler() {
+  uint32_t* pool = sched_pool();
+  if (pool == nullptr) return -12;
+  return (int)cudaMemset(pool, 0, kSchedSlots * 128);
 }
 
-// co-resident 4-CTA clusters (GPC boundaries can leave SMs unusable for a cluster): queried once
-static int gemm4_max_clusters(int smem_bytes) {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kNumSMs / 4 * 4, 1, 1);
-  cfg.blockDim = dim3(kGemm2Threads, 1, 1);
-  cfg.dynamicSmemBytes = smem_bytes;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm4_tcgen05_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-  cached = n;
-  return cached;
-}
-
-static int launch_gemm4(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_sms, cudaStream_t st) {
-  constexpr int kSmem = kStages2 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm4_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  const int tiles = ((p.M + 511) / 512) * ((p.N + 255) / 256);
-  int clusters = std::min(std::min(tiles, num_sms / 4), gemm4_max_clusters(kSmem));
-  if (clusters <= 0) return -30;
-  gemm4_tcgen05_kernel<<<clusters * 4, kGemm2Threads, kSmem, st>>>(ma, mb, p);
-  return EPL_CHECK_LAUNCH();
-}
-
-extern "C" int epl_gemm4_max_clusters() {
-  constexpr int kSmem = kStages2 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 256;
-  cudaFuncSetAttribute(gemm4_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  return gemm4_max_clusters(kSmem);
-}
-
-static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_sms, cudaStream_t st) {
+static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, int num_sms, cudaStream_t st) {
   constexpr int kSmem = kStages2 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 256;
   static bool configured = false;
   if (!configured) {
@@ -1146,6 +1071,8 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const Gemm
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
+  p.sched_counter = sched_counter_for(st);
+  if (p.sched_counter == nullptr) return -12;
   const int tiles = ((p.M + 255) / 256) * ((p.N + p.bn2 - 1) / p.bn2);
   int clusters = std::min(tiles, num_sms / 2);
   gemm2_tcgen05_kernel<<<clusters * 2, kGemm2Threads, kSmem, st>>>(ma, mb, p);
@@ -1195,18 +1122,6 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
   // The 2-CTA kernel (cta_group::2, 256 x {128,192,256} tiles) is the default whenever the problem spans at least one
   // such tile: measured +8-12 % over the 1-CTA 128x256 kernel on every GPT-2-XL shape
   // (profiles/r1_gemm_bench_v2_with_2cta.txt).  force_bn: 0 = pick the width per shape, 512 / 448 / 384 = force 256 / 192 / 128.
-  if (force_bn == 1024 && M >= 512 && N >= 256) {             // 4-CTA cluster, B tile multicast across two pairs
-    CUtensorMap ma4, mb4;
-    int rc4 = !a_mn_major ? make_map_2d(&ma4, A, M, K, lda, BLOCK_K, BLOCK_M, is_fp16) : make_map_2d(&ma4, A, K, M, lda, 64, BLOCK_K, is_fp16);
-    if (rc4) return rc4;
-    rc4 = !b_mn_major ? make_map_2d(&mb4, B, N, K, ldb, BLOCK_K, 64, is_fp16) : make_map_2d(&mb4, B, K, N, ldb, 64, BLOCK_K, is_fp16);
-    if (rc4) return rc4;
-    GemmParams p4;
-    p4.M = M; p4.N = N; p4.K = K; p4.ldd = ldd; p4.D = D; p4.bias = bias; p4.pre = pre; p4.aux = aux; p4.epilogue = epilogue;
-    p4.accumulate = accumulate; p4.out_dtype = out_dtype; p4.a_mn_major = a_mn_major; p4.b_mn_major = b_mn_major; p4.alpha = alpha;
-    p4.ab_format = is_fp16 ? 0 : 1; p4.bn2 = 256;
-    return launch_gemm4(ma4, mb4, p4, num_sms > 0 ? num_sms : kNumSMs, (cudaStream_t)stream);
-  }
   const bool two_cta_forced = force_bn == 512 || force_bn == 448 || force_bn == 384;
   if ((two_cta_forced || force_bn == 0) && M >= 256 && N >= 256) {
     const int sms = num_sms > 0 ? num_sms : kNumSMs;

@@ -177,6 +177,169 @@ __global__ void __launch_bounds__(512, 1) fused_rs_adam_ag_kernel(const FusedDpA
   barrier_end(a);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K1 v2 — the same reduce-scatter + AdamW + all-gather, restructured so that it can run on a handful of SMs next
+// to the backward GEMMs (and at full NVLink rate on the whole GPU for the last bucket):
+//   * peer gradients do not travel through registers: one thread per CTA streams 4 KB pieces of every peer's
+//     gradient shard into a shared-memory ring with cp.async.bulk (completion on an mbarrier), so the bytes in
+//     flight per CTA (kStages-1 stages x W x 4 KB) are independent of the thread count — 8 CTAs keep ~0.7 MB
+//     outstanding, the v1 kernel needed all 148 SMs x 512 threads for the same;
+//   * the new weights are staged in shared memory (3 x 4 KB) and leave as W bulk stores per piece
+//     (cp.async.bulk.global.shared::cta) — in- and outbound NVLink traffic overlap inside every CTA;
+//   * the reduction order is fixed (rank 0 .. W-1) so the result is bit-reproducible against an fp32 reference;
+//   * hyper-parameters that change every step (lr, bias corrections, gradient scale) and the barrier epoch are
+//     read from device memory (`dyn`), so the launch can be replayed from a CUDA graph.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kK1Piece = 2048;                    // elements per piece (4 KB of bf16 per peer)
+constexpr int kK1Threads = kK1Piece / 8;          // one 16-byte vector per thread per piece
+constexpr int kK1OutBufs = 3;
+
+struct FusedDpDyn {                               // device-resident, updated by a tiny kernel / memcpy before each step
+  float lr, inv_c1, inv_c2, grad_scale;
+};
+
+EPL_DEVICE void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+EPL_DEVICE void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+template <typename G, bool kHasMask>
+__global__ void __launch_bounds__(kK1Threads, 1) fused_rs_adam_ag_v2_kernel(const FusedDpArgs a, const FusedDpDyn* __restrict__ dyn,
+                                                                         int stages) {
+  extern __shared__ __align__(128) unsigned char k1_smem[];
+  const int W = a.world;
+  const uint32_t stage_bytes = (uint32_t)W * kK1Piece * 2;
+  unsigned char* ring = k1_smem;                                            // [stages][W][4 KB]
+  unsigned char* obuf = ring + (size_t)stages * stage_bytes;               // [kK1OutBufs][4 KB]
+  uint64_t* full = reinterpret_cast<uint64_t*>(obuf + kK1OutBufs * kK1Piece * 2);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  // epoch 0 = take it from device memory (local_sync[2] holds the epoch of the previous launch on this bucket): the launch
+  // carries no per-step host value and can be replayed from a CUDA graph
+  FusedDpArgs aa = a;
+  if (aa.epoch == 0) aa.epoch = *reinterpret_cast<volatile uint32_t*>(a.local_sync + 2) + 1u;
+  barrier_start(aa);                                                        // (contains __syncthreads)
+  const float lr = dyn->lr, inv_c1 = dyn->inv_c1, inv_c2 = dyn->inv_c2, gscale = dyn->grad_scale;
+  const int64_t npieces = (a.shard_n + kK1Piece - 1) / kK1Piece;
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  const int64_t mine = first < npieces ? (npieces - first + step - 1) / step : 0;   // pieces of this CTA
+
+  auto issue = [&](int64_t jl) {                                            // thread 0: loads of local piece index jl
+    const int64_t piece = first + jl * step;
+    const int64_t e0 = piece * kK1Piece;
+    const uint32_t bytes = (uint32_t)(min((int64_t)kK1Piece, a.shard_n - e0) * 2);
+    const int slot = (int)(jl % stages);
+    mbar_expect_tx(&full[slot], bytes * (uint32_t)W);
+    for (int p = 0; p < W; ++p) {
+      const int src = (a.rank + p) % W;                                     // issue order rotated: all links busy at once
+      bulk_g2s(ring + (size_t)slot * stage_bytes + (size_t)src * (kK1Piece * 2),
+               reinterpret_cast<const G*>(a.grads.ptr[src]) + a.shard_start + e0, bytes, &full[slot]);
+    }
+  };
+  if (tid == 0) for (int64_t jl = 0; jl < min(mine, (int64_t)stages - 1); ++jl) issue(jl);
+
+  // optimizer state of the NEXT piece is requested one iteration ahead (register double buffer): its HBM latency overlaps the
+  // current piece's reduction + AdamW instead of being exposed once per piece (measured before: 2 us per 4 KB piece per CTA)
+  float4 nx[8];
+  auto load_state = [&](int64_t jl_) {
+    const int64_t e0_ = (first + jl_ * step) * kK1Piece;
+    const int nvec_ = (int)(min((int64_t)kK1Piece, a.shard_n - e0_) >> 3);
+    if (tid < nvec_) {
+      const int64_t i_ = (e0_ >> 3) + tid;
+      nx[0] = reinterpret_cast<const float4*>(a.master)[2 * i_]; nx[1] = reinterpret_cast<const float4*>(a.master)[2 * i_ + 1];
+      nx[2] = reinterpret_cast<const float4*>(a.m)[2 * i_]; nx[3] = reinterpret_cast<const float4*>(a.m)[2 * i_ + 1];
+      nx[4] = reinterpret_cast<const float4*>(a.v)[2 * i_]; nx[5] = reinterpret_cast<const float4*>(a.v)[2 * i_ + 1];
+      if constexpr (kHasMask) { nx[6] = reinterpret_cast<const float4*>(a.mask)[2 * i_]; nx[7] = reinterpret_cast<const float4*>(a.mask)[2 * i_ + 1]; }
+    }
+  };
+  if (mine > 0) load_state(0);
+  for (int64_t jl = 0; jl < mine; ++jl) {
+    const int64_t piece = first + jl * step;
+    const int64_t e0 = piece * kK1Piece;
+    const int nvec = (int)(min((int64_t)kK1Piece, a.shard_n - e0) >> 3);
+    const int slot = (int)(jl % stages);
+    const uint32_t phase = (uint32_t)((jl / stages) & 1);
+    const bool active = tid < nvec;
+    const int64_t i = (e0 >> 3) + tid;                                      // 8-element vector index inside the shard
+    const float4 p0 = nx[0], p1 = nx[1], m0 = nx[2], m1 = nx[3], v0 = nx[4], v1 = nx[5], k0 = nx[6], k1 = nx[7];
+    if (jl + 1 < mine) load_state(jl + 1);
+    if (tid == 0 && jl + stages - 1 < mine) issue(jl + stages - 1);        // refill the slot consumed in the previous iteration
+    mbar_wait(&full[slot], phase);
+    unsigned char* ob = obuf + (size_t)(jl % kK1OutBufs) * (kK1Piece * 2);
+    if (active) {
+      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const unsigned char* st = ring + (size_t)slot * stage_bytes + (size_t)tid * 16;
+      for (int src = 0; src < W; ++src) accumulate8<G>(g, *reinterpret_cast<const int4*>(st + (size_t)src * (kK1Piece * 2)));
+      float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float kk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if constexpr (kHasMask) { kk[0] = k0.x; kk[1] = k0.y; kk[2] = k0.z; kk[3] = k0.w; kk[4] = k1.x; kk[5] = k1.y; kk[6] = k1.z; kk[7] = k1.w; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gr = g[j] * gscale;
+        mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * gr;
+        vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * gr * gr;
+        pp[j] -= lr * ((mm[j] * inv_c1) / (sqrtf(vv[j] * inv_c2) + a.eps) + a.weight_decay * kk[j] * pp[j]);
+      }
+      reinterpret_cast<float4*>(a.master)[2 * i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      reinterpret_cast<float4*>(a.master)[2 * i + 1] = make_float4(pp[4], pp[5], pp[6], pp[7]);
+      reinterpret_cast<float4*>(a.m)[2 * i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(a.m)[2 * i + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
+      reinterpret_cast<float4*>(a.v)[2 * i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      reinterpret_cast<float4*>(a.v)[2 * i + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+      uint32_t packed[4];
+      if constexpr (std::is_same<G, __nv_bfloat16>::value) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) packed[j] = pack_bf16x2(pp[2 * j], pp[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { __half2 h = __floats2half2_rn(pp[2 * j], pp[2 * j + 1]); packed[j] = *reinterpret_cast<uint32_t*>(&h); }
+      }
+      *reinterpret_cast<int4*>(ob + (size_t)tid * 16) = make_int4((int)packed[0], (int)packed[1], (int)packed[2], (int)packed[3]);
+    }
+    fence_proxy_async();                                                    // staged weights -> visible to the bulk-copy engine
+    __syncthreads();                                                        // ring slot consumed by everyone, staging complete
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)nvec * 16;
+      for (int p = 0; p < W; ++p) {
+        const int dst = (a.rank + p) % W;
+        bulk_s2g(reinterpret_cast<G*>(a.params.ptr[dst]) + a.shard_start + e0, ob, bytes);
+      }
+      tma_store_commit();
+      tma_store_wait_read<1>();                                             // the staging buffer of the previous piece is free again
+    }
+  }
+  if (tid == 0) {
+    tma_store_wait<0>();                                                    // every weight store of this CTA has been performed
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  // end barrier; unlike v1 the arrival counter is reset by the last CTA, so the grid size may change between launches
+  __syncthreads();
+  __shared__ int is_last;
+  if (tid == 0) {
+    __threadfence_system();
+    is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (tid < W) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[tid]) + kMaxPeers + a.rank, aa.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + kMaxPeers + tid) < aa.epoch) {}
+    }
+    __syncthreads();
+    if (tid == 0) { a.local_sync[1] = 0u; a.local_sync[2] = aa.epoch; __threadfence(); }
+  }
+}
+
 // Stand-alone device barrier over the same flag protocol (used by tests and by the Python engine between phases)
 __global__ void symm_barrier_kernel(PeerTable flags, int rank, int world, uint32_t epoch) {
   if (threadIdx.x < world) {
@@ -260,6 +423,58 @@ int epl_fused_rs_adam_ag(void* const* grad_ptrs, void* const* param_ptrs, void* 
   } else {
     return -1;
   }
+  return EPL_CHECK_LAUNCH();
+}
+
+// v2: bulk-copy ring; `dyn` = device pointer to {lr, inv_c1, inv_c2, grad_scale}; epoch is still a launch argument
+// (a graph-captured launch bumps it with epl_symm_epoch_add on the flags instead, see below).
+int epl_fused_rs_adam_ag_v2(void* const* grad_ptrs, void* const* param_ptrs, void* const* flag_ptrs, void* local_sync,
+                            void* master, void* m, void* v, const void* mask, int64_t shard_start, int64_t shard_n,
+                            int rank, int world, unsigned epoch, int dtype, const void* dyn, float beta1, float beta2, float eps,
+                            float weight_decay, int blocks, void* stream) {
+  if (world > kMaxPeers || (shard_n & 7) || (shard_start & 7)) return -20;
+  FusedDpArgs a;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    a.grads.ptr[i] = i < world ? grad_ptrs[i] : nullptr;
+    a.params.ptr[i] = i < world ? param_ptrs[i] : nullptr;
+    a.flags.ptr[i] = i < world ? flag_ptrs[i] : nullptr;
+  }
+  a.local_sync = (uint32_t*)local_sync;
+  a.master = (float*)master; a.m = (float*)m; a.v = (float*)v; a.mask = (const float*)mask;
+  a.shard_start = shard_start; a.shard_n = shard_n; a.rank = rank; a.world = world; a.epoch = epoch;
+  a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = 1.f;
+  a.inv_c1 = a.inv_c2 = 1.f;
+  const int stage_bytes = world * kK1Piece * 2;
+  int stages = std::max(2, std::min(8, (128 * 1024) / stage_bytes));
+  const int smem = stages * stage_bytes + kK1OutBufs * kK1Piece * 2 + 128;
+  const int64_t npieces = (shard_n + kK1Piece - 1) / kK1Piece;
+  if (blocks <= 0) blocks = kNumSMs;
+  blocks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(blocks, kNumSMs), npieces));
+  // CTAs are launched as pairs (cluster of 2 = one TPC) so that a small grid running next to the backward GEMMs takes whole
+  // TPCs and leaves the GEMM's CTA pairs (cta_group::2 needs both SMs of a TPC) a clean set of SMs
+  cudaStream_t st = (cudaStream_t)stream;
+#define EPL_K1V2(G, MASK)                                                                                              \
+  do {                                                                                                                 \
+    static bool configured = false;                                                                                    \
+    if (!configured) {                                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(fused_rs_adam_ag_v2_kernel<G, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           128 * 1024 + kK1OutBufs * kK1Piece * 2 + 128);                               \
+      if (e != cudaSuccess) return (int)e;                                                                             \
+      configured = true;                                                                                               \
+    }                                                                                                                  \
+    cudaLaunchConfig_t cfg = {};                                                                                       \
+    cfg.gridDim = dim3(blocks, 1, 1); cfg.blockDim = dim3(kK1Threads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
+    cudaLaunchAttribute attr[1];                                                                                       \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                  \
+    attr[0].val.clusterDim.x = (blocks % 2 == 0) ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                                                \
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fused_rs_adam_ag_v2_kernel<G, MASK>, a, (const FusedDpDyn*)dyn, stages);  \
+    if (le != cudaSuccess) return (int)le;                                                                             \
+  } while (0)
+  if (dtype == EPL_BF16) { if (mask) EPL_K1V2(__nv_bfloat16, true); else EPL_K1V2(__nv_bfloat16, false); }
+  else if (dtype == EPL_F16) { if (mask) EPL_K1V2(__half, true); else EPL_K1V2(__half, false); }
+  else return -1;
+#undef EPL_K1V2
   return EPL_CHECK_LAUNCH();
 }
 

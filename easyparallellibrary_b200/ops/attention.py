@@ -34,6 +34,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = 
 
 def attention_packed(qkv: torch.Tensor, causal: bool = True) -> torch.Tensor:
   """``qkv``: ``[B, S, 3, H, D]`` (output of a fused QKV projection) -> ``[B, S, H*D]``."""
+  from easyparallellibrary_b200.runtime import amp
+  if amp.o1_active():
+    qkv = amp.cast_args("attention", qkv)
   if _IMPL != "sdpa" and qkv.is_cuda:
     from easyparallellibrary_b200.ops import attention_kernel
     if attention_kernel.supported_packed(qkv):

@@ -45,6 +45,9 @@ class _XentFn(torch.autograd.Function):
 def softmax_cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100,
                           reduction: str = "mean") -> torch.Tensor:
   """Note: on CUDA the logits buffer is consumed (overwritten with its gradient)."""
+  from easyparallellibrary_b200.runtime import amp
+  if amp.o1_active():                            # O1 deny-list op
+    logits = amp.cast_args("cross_entropy", logits)
   V = logits.shape[-1]
   if logits.is_cuda and V * logits.element_size() <= 200 * 1024 and logits.stride(-1) == 1 \
       and (logits.numel() // V == 0 or logits.view(-1, V).stride(0) % (16 // logits.element_size()) == 0):

@@ -52,7 +52,15 @@ class _NormFn(torch.autograd.Function):
     return dx.view(ctx.shape), dgamma, dbeta, None, None, None
 
 
+def _o1(x, gamma, beta):
+  from easyparallellibrary_b200.runtime import amp
+  if amp.o1_active():                            # O1 deny-list op: statistics and output in fp32
+    return amp.cast_args("layer_norm", x, gamma, beta)
+  return x, gamma, beta
+
+
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+  x, gamma, beta = _o1(x, gamma, beta)
   if x.is_cuda and x.shape[-1] % (16 // x.element_size()) == 0:
     return _NormFn.apply(x, gamma, beta, eps, False)
   return torch.nn.functional.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
@@ -61,12 +69,14 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor
 def layer_norm_fork(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor], eps: float = 1e-5):
   """Returns ``(x, LN(x))`` for a pre-LN residual block.  The backward kernel adds the gradient arriving on the
   skip connection to the LayerNorm input gradient in the same pass (no stand-alone add kernel)."""
+  x, gamma, beta = _o1(x, gamma, beta)
   if x.is_cuda and x.shape[-1] % (16 // x.element_size()) == 0:
     return _NormFn.apply(x, gamma, beta, eps, False, True)
   return x, torch.nn.functional.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
 
 
 def rms_norm(x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+  x, gamma, _ = _o1(x, gamma, None)
   if x.is_cuda and x.shape[-1] % (16 // x.element_size()) == 0:
     return _NormFn.apply(x, gamma, None, eps, True)
   xf = x.float()

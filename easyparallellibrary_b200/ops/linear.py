@@ -86,7 +86,11 @@ def _sink_weight_grad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> Opti
   parameter (``epl_main_grad``) the GEMM accumulates straight into it (no autograd add pass)."""
   sink = getattr(w, "epl_main_grad", None)
   if sink is not None and sink.dtype in (torch.bfloat16, torch.float16, torch.float32):
-    gemm(a, b, a_mn_major=True, b_mn_major=True, out=sink.view(w.shape), accumulate=True)
+    # first contribution of the step to a weight with a single use: plain store (no read-modify-write of the bucket)
+    fresh = getattr(w, "epl_sink_fresh", False)
+    if fresh:
+      w.epl_sink_fresh = False
+    gemm(a, b, a_mn_major=True, b_mn_major=True, out=sink.view(w.shape), accumulate=not fresh)
     ready = getattr(w, "epl_grad_ready", None)
     if ready is not None:
       ready(w)
@@ -227,6 +231,9 @@ def _resolve_pending(x: torch.Tensor, w: torch.Tensor, fusable: bool):
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False,
            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
   """``y = x @ w^T (+ bias) (GELU)`` or, with ``residual``, ``y = residual + x @ w^T + bias`` — one kernel either way."""
+  from easyparallellibrary_b200.runtime import amp
+  if amp.o1_active():                            # O1 allow-list op: fp16 inputs, fp32 weights cast just in time
+    x, w, bias, residual = amp.cast_args("linear", x, w, bias, residual)
   pend = _resolve_pending(x, w, fusable=residual is None)
   if pend is not None:
     return _GatherLinearFn.apply(x, w, bias, gelu, pend)
@@ -239,6 +246,9 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def mlp(x, w1, b1, w2, b2, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+  from easyparallellibrary_b200.runtime import amp
+  if amp.o1_active():
+    x, w1, b1, w2, b2, residual = amp.cast_args("mlp", x, w1, b1, w2, b2, residual)
   _resolve_pending(x, w1, fusable=False)          # the fused MLP block keeps its own kernels: gather a deferred weight first
   if _use_kernel(x, w1) and w2.shape[0] % 8 == 0:
     return _MlpFn.apply(x, w1, b1, w2, b2, residual)

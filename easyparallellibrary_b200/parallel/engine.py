@@ -154,6 +154,8 @@ class Trainer(object):
 
     # ---- precision, placement, recompute ---------------------------------------------
     self.compute_dtype = amp_lib.compute_dtype(cfg.amp.level)
+    self.o1 = (cfg.amp.level or "").lower() == "o1"       # fp32 parameters, per-op fp16/fp32 policy (runtime/amp.py)
+    env.parallel_plan = self.plan
     for m in local:
       if self.compute_dtype is not None:
         amp_lib.cast_module(m, self.compute_dtype, cfg.amp.debug_log)
@@ -198,6 +200,15 @@ class Trainer(object):
     group_params: Dict[int, List[nn.Parameter]] = {}
     group_ranks: Dict[int, List[int]] = {}
     seen = set()
+    # parameters whose gradient is sparse (nn.Embedding(sparse=True)): kept out of the dense flat buckets; their gradients
+    # travel as (indices, values) all-gathers (reference rewriters/sparse_allreduce.py:127-160) unless
+    # communication.sparse_as_dense densifies them first (reference parallel/hooks.py:162-167)
+    sparse_ids = set()
+    for mod in self.stage_modules.values():
+      for m in mod.modules():
+        if isinstance(m, (nn.Embedding, nn.EmbeddingBag)) and getattr(m, "sparse", False):
+          sparse_ids.add(id(m.weight))
+    self._sparse: Dict[int, List[Tuple[nn.Parameter, FlatOptimizer]]] = {}
     for s in self.plan.local_stages:
       pl = self.plan.placements[self.plan.stage_taskgraphs[s]]
       mine = []
@@ -205,6 +216,9 @@ class Trainer(object):
         if id(p) in seen or not p.requires_grad:
           continue
         seen.add(id(p))
+        if id(p) in sparse_ids:
+          self._sparse.setdefault(s, []).append(p)
+          continue
         ti = split_owner.get(id(p))
         if ti is not None and ti in self.plan.placements:
           key = 1000 + ti
@@ -216,6 +230,12 @@ class Trainer(object):
       group_params[s], group_ranks[s] = mine, pl.dp_ranks
     self.group_keys = [k for k in list(self.plan.local_stages) + sorted(k for k in group_params if k >= 1000)]
     self.has_split = any(k >= 1000 for k in self.group_keys)
+    from easyparallellibrary_b200.ops.tensor_parallel import Replica2Split
+    self._split_gathers_batch = any(isinstance(m, Replica2Split) and (m.group is None or m.group.size > 1)
+                                    for mod in self.stage_modules.values() for m in mod.modules())
+    self._split_size = 1
+    for ti in self.plan.split_taskgraphs:
+      self._split_size = max(self._split_size, graph.taskgraphs[ti].strategy.device_count or self.plan.world)
     extra = []
     for ti in self.plan.split_taskgraphs:       # every rank registers every shard-replica group (collective creation)
       n = graph.taskgraphs[ti].strategy.device_count or self.plan.world
@@ -244,7 +264,9 @@ class Trainer(object):
           units = [root]                         # parameters live directly on the root: treat it as one unit
         self.zero3[s] = Zero3Engine(self, s, units, comm)
         params = []
-      flat = FlatParameters(params, cfg.communication.max_splits, shard_world, allocator=self._bucket_allocator(comm))
+      allocator = self._bucket_allocator(comm)
+      splits = max(cfg.communication.max_splits, cfg.communication.fused_splits) if allocator is not None else cfg.communication.max_splits
+      flat = FlatParameters(params, splits, shard_world, allocator=allocator)
       self.flats[s] = flat
       if comm.size > 1:
         for dt, buf in flat.flat_params.items():
@@ -267,6 +289,15 @@ class Trainer(object):
         else:
           opts.append(FlatOptimizer(self.opt_kind, self.hyper, master, None if mask is None else mask[lo:hi]))
       self.optimizers[s] = opts
+    for s_, plist in list(self._sparse.items()):
+      items = []
+      for p in plist:
+        if self.dp_comms[s_].size > 1:
+          self.dp_comms[s_].broadcast(p.data, root=0)
+        master = p.data.view(-1) if p.dtype == torch.float32 else p.data.view(-1).to(torch.float32)
+        mask = None if not self.no_decay(p) else torch.zeros(p.numel(), dtype=torch.float32, device=p.device)
+        items.append((p, FlatOptimizer(self.opt_kind, self.hyper, master, mask)))
+      self._sparse[s_] = items
     self._setup_fused(cfg)
     self._install_grad_hooks()
     if self.plan.pipeline:
@@ -375,8 +406,16 @@ class Trainer(object):
     self._first_micro_batch = True
     self._last_micro_batch = True
     self._mean = True
+    # a parameter referenced from several places (tied embeddings: the LM head multiplies by wte.weight) receives several
+    # gradient contributions per backward; such a parameter is "ready" only when autograd has accumulated the last one
+    uses: Dict[int, int] = {}
+    for m in self.stage_modules.values():
+      for _, p in m.named_parameters(remove_duplicate=False):
+        uses[id(p)] = uses.get(id(p), 0) + 1
+    self._sink_params: List[nn.Parameter] = []
     for s, flat in self.flats.items():
       for b in flat.buckets:
+        b.ready_ids = set()
         for p, o in zip(b.params, b.offsets):
           self._bucket_of[id(p)] = (s, b, o)
           view = b.flat_grad[o:o + p.numel()].view(p.shape)      # the buckets are persistent: build the view once, not per hook call
@@ -385,8 +424,13 @@ class Trainer(object):
           if p.is_cuda and b.flat_grad.dtype == p.dtype:
             # weight-gradient GEMMs accumulate straight into the flat bucket (ops/linear.py:_sink_weight_grad)
             p.epl_main_grad = b.flat_grad[o:o + p.numel()]
-            p.epl_grad_ready = self._on_grad_ready
+            if uses.get(id(p), 1) <= 1 and not getattr(p, "epl_shared", False):
+              # exactly one contribution: the GEMM itself reports readiness (autograd sees no gradient for this weight) and
+              # the first micro-batch's GEMM may store instead of accumulate (epl_sink_fresh, re-armed every step)
+              p.epl_grad_ready = self._on_grad_ready
+              self._sink_params.append(p)
     self._pending: List[Tuple[int, Bucket, Any]] = []
+    self._launched_buckets = set()
 
   def _on_grad_ready(self, p: nn.Parameter) -> None:
     s, b, o = self._bucket_of[id(p)]
@@ -397,10 +441,15 @@ class Trainer(object):
         view.add_(g)
         p.grad = view if view.dtype == p.dtype else None
     b.ready += 1
-    if self._last_micro_batch and b.ready % len(b.params) == 0:
+    b.ready_ids.add(id(p))
+    if len(b.ready_ids) == len(b.params) and not self._last_micro_batch:
+      b.ready_ids = set()                          # complete for this micro-batch: count again for the next one
+    elif len(b.ready_ids) == len(b.params) and (s, b.index) not in self._launched_buckets:
       if self.fused is not None and self.fused.overlap and not self.plan.pipeline and self.max_grad_norm is None:
-        self.fused.launch_bucket_async(s, b.index, self._mean and not self.has_split)
+        self._launched_buckets.add((s, b.index))
+        self.fused.launch_bucket_async(s, b.index)
       elif self._overlap:
+        self._launched_buckets.add((s, b.index))
         self._launch_bucket_reduce(s, b)
 
   # ================================================================== one step
@@ -420,6 +469,14 @@ class Trainer(object):
     for z in self.zero3.values():
       z.zero_grad()
     self._pending = []
+    self._launched_buckets = set()
+    for flat in self.flats.values():
+      for b in flat.buckets:
+        b.ready_ids = set()
+    for p in self._sink_params:
+      p.epl_sink_fresh = True
+    if self.fused is not None:
+      self.fused.begin_step(mean)
     batch = tuple(_to_device(x, self.device) for x in batch)
     if self.compute_dtype is not None and batch and isinstance(batch[0], torch.Tensor) and batch[0].is_floating_point():
       batch = (batch[0].to(self.compute_dtype),) + batch[1:]          # the model input follows the compute dtype (AMP)
@@ -429,22 +486,26 @@ class Trainer(object):
     dp_size = max(c.size for c in self.dp_comms.values()) if self.dp_comms else 1
     self._overlap = (dp_size > 1 and not cfg.communication.clip_after_allreduce and self.max_grad_norm is None
                      and self.fused is None)
-    if self.plan.pipeline:
-      losses, collected = self.pipe.run(micro, mean)
-    else:
-      for i, mb in enumerate(micro):
-        self._first_micro_batch = i == 0
-        self._last_micro_batch = i == M - 1
-        graph.current_micro_batch = mb
-        with phase_scope(ModelPhase.FORWARD):
-          loss = self._forward_loss(mb, kwargs)
-        collected.append(graph.pop_collections())
-        losses.append(loss.detach())
-        scaled = self.scaler.scale(loss)
-        if mean and M > 1:
-          scaled = scaled / M
-        with phase_scope(ModelPhase.BACKWARD):
-          scaled.backward()
+    if cfg.gradient_checkpoint.check_gradients and cfg.gradient_checkpoint.type and not getattr(self, "_gc_checked", False):
+      self._gc_checked = True
+      self._check_recompute_gradients(micro[0], kwargs)
+    with amp_lib.o1_autocast(self.device.type, enabled=self.o1, debug_log=cfg.amp.debug_log):
+      if self.plan.pipeline:
+        losses, collected = self.pipe.run(micro, mean)
+      else:
+        for i, mb in enumerate(micro):
+          self._first_micro_batch = i == 0
+          self._last_micro_batch = i == M - 1
+          graph.current_micro_batch = mb
+          with phase_scope(ModelPhase.FORWARD):
+            loss = self._forward_loss(mb, kwargs)
+          collected.append(graph.pop_collections())
+          losses.append(loss.detach())
+          scaled = self.scaler.scale(loss)
+          if mean and M > 1:
+            scaled = scaled / M
+          with phase_scope(ModelPhase.BACKWARD):
+            scaled.backward()
     for z in self.zero3.values():
       z.finish_backward()
     with phase_scope(ModelPhase.APPLY):
@@ -458,6 +519,45 @@ class Trainer(object):
     for h in self.hooks:
       h.after_step(self, out)
     return out
+
+  def _check_recompute_gradients(self, mb: Tuple[Any, ...], kwargs) -> None:
+    """``gradient_checkpoint.check_gradients`` (reference gc/gradient_checkpoint.py:310-325): before the first step, the
+    gradients of one micro-batch are computed with and without recomputation and compared; a mismatch (a segment that is not
+    a pure function of its inputs: unseeded randomness, in-place state) raises instead of training on wrong gradients."""
+    from easyparallellibrary_b200.runtime import gradient_checkpoint as gc_lib
+    if self.plan.pipeline or self.zero3:
+      get_logger().warning("gradient_checkpoint.check_gradients: skipped (pipeline / ZeRO-3 stages own their backward)")
+      return
+    saved_last, self._last_micro_batch = self._last_micro_batch, False      # no bucket may be launched from the hooks
+    snaps = []
+    try:
+      for enabled in (False, True):
+        gc_lib.RECOMPUTE_ENABLED = enabled
+        for flat in self.flats.values():
+          flat.zero_grad()
+        for p in self._sink_params:
+          p.epl_sink_fresh = True
+        with amp_lib.o1_autocast(self.device.type, enabled=self.o1):
+          self._forward_loss(mb, kwargs).backward()
+        snaps.append([g.detach().float().clone() for flat in self.flats.values() for g in flat.flat_grads.values()])
+    finally:
+      gc_lib.RECOMPUTE_ENABLED = True
+      self._last_micro_batch = saved_last
+    worst = 0.0
+    for a, b in zip(*snaps):
+      worst = max(worst, float((a - b).abs().max() / (a.abs().max() + 1e-12)))
+    tol = 1e-5 if self.compute_dtype is None and not self.o1 else 2e-2
+    get_logger().info("gradient checkpoint check: max relative gradient difference %.3e (tolerance %.1e)", worst, tol)
+    if not worst <= tol:
+      raise RuntimeError("gradient_checkpoint.check_gradients: recomputed gradients differ from plain ones (max relative "
+                         "difference %.3e > %.1e)" % (worst, tol))
+    for flat in self.flats.values():
+      flat.zero_grad()
+      for b in flat.buckets:
+        b.ready_ids = set()
+    for p in self._sink_params:
+      p.epl_sink_fresh = True
+    self.gc_check_result = worst
 
   def _forward_loss(self, mb: Tuple[Any, ...], kwargs) -> torch.Tensor:
     if self.plan.num_stages > 1:          # colocated stages: run them back to back
@@ -478,6 +578,14 @@ class Trainer(object):
     slot = len(self._pending) % comm.pool.size
     be = comm.pool.backends[slot]
     zero = self.config.zero.level
+    ccfg = self.config.communication
+    if ccfg.fp16 and b.flat_grad.dtype == torch.float32:
+      # 16-bit wire format for fp32 gradients (reference coalescing.py:341-342,374-378: cast(grad * fp16_scale) before the
+      # all-reduce, cast back and divide after): halves the bytes on the link; the decompression runs when the reduce is waited on
+      wire = (b.flat_grad * float(ccfg.fp16_scale)).to(torch.float16)
+      w = be.all_reduce_async(wire, "sum")
+      self._pending.append((s, b, _Decompress(w, wire, b.flat_grad, float(ccfg.fp16_scale))))
+      return
     if self._sharded[s] and zero != "v0":
       lo, hi = b.shard_range(comm.rank, comm.size)
       w = be.reduce_scatter_into(b.flat_grad[lo:hi], b.flat_grad, "sum", async_op=True)
@@ -492,15 +600,20 @@ class Trainer(object):
     gnorm = None
     # (1) clip-then-reduce: local norm, local clip coefficient folded into the grad scale
     local_coef = 1.0
+    local_coef_applied = 1.0            # sparse gradients are not stored in the buckets: their clip coefficient rides on the scale
     if self.max_grad_norm is not None and not clip_after:
       gnorm = self._grad_norm(reduced=False) * inv
       c = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
+      local_coef_applied = c
       if c < 1.0:                       # each replica clips its own gradient, then the clipped ones are reduced
         for s_ in self.group_keys:
           for g_ in self.flats[s_].flat_grads.values():
             g_.mul_(c)
+          if s_ in self.zero3:           # ZeRO-3 gradients live in the units' shards (already reduce-scattered)
+            self.zero3[s_].scale_grads(c)
     if self.fused is not None:          # the gradient buckets live in symmetric memory: the fused kernel reads the clipped values
       skipped, _ = self.fused.reduce_and_apply(mean)
+      self._reduce_apply_sparse(mean, inv * local_coef_applied)
       return skipped, gnorm
     # (2) reduce, last bucket first (its gradients were produced first)
     launched = {(s, b.index) for s, b, _ in self._pending}
@@ -531,19 +644,63 @@ class Trainer(object):
     # (4) reduce-then-clip
     coef = local_coef
     if self.max_grad_norm is not None and clip_after:
-      n = max(c.size for c in self.dp_comms.values())
+      n = max(self.mean_divisor(s_) for s_ in self.group_keys)
       gnorm = self._grad_norm(reduced=True) * inv / (n if mean else 1)
       coef = float(min(1.0, self.max_grad_norm / (float(gnorm) + 1e-6)))
     # (5) apply
     for s in self.group_keys:
       self._apply_group(s, mean, inv * coef)
+    self._reduce_apply_sparse(mean, inv * coef * local_coef_applied)
     return False, gnorm
+
+  def _reduce_apply_sparse(self, mean: bool, scale0: float) -> None:
+    if not self._sparse:
+      return
+    from easyparallellibrary_b200.communicators.sparse import sparse_all_reduce
+    densify = self.config.communication.sparse_as_dense
+    for s, items in self._sparse.items():
+      comm = self.dp_comms[s]
+      scale = scale0 / (self.mean_divisor(s) if mean else 1)
+      for p, opt in items:
+        g = p.grad
+        if g is None:
+          continue
+        if g.is_sparse:
+          if densify:
+            g = g.to_dense()
+            if comm.size > 1:
+              comm.primary.all_reduce(g, "sum")
+          else:
+            if comm.size > 1:
+              g = sparse_all_reduce(comm, g)            # all-gather of indices and values: bytes ~ touched rows, not the table
+            self.sparse_wire_elems = getattr(self, "sparse_wire_elems", 0) + int(g._nnz()) * int(g.shape[1] if g.dim() > 1 else 1)
+            g = g.to_dense()
+        elif comm.size > 1:
+          comm.primary.all_reduce(g, "sum")
+        opt.step(g.reshape(-1), p.data.view(-1), scale)
+        p.grad = None
+
+  def mean_divisor(self, s: int) -> int:
+    """Number of independent data replicas whose (already batch-averaged) losses this group's reduction sums.
+
+    Plain data parallelism: the group size.  Megatron-style tensor parallelism (``split(n)`` on k*n GPUs, the n ranks of a
+    group see the same batch): still the group size — shard groups have k members, one per data replica; replicated
+    parameters are reduced over all k*n ranks and every replica's gradient appears n times in that sum.  ``Replica2Split``
+    bridges (the reference's colocated split head, ``bridging_layer.py:46-58``): every rank feeds its own batch, the n
+    batches are gathered and the loss is the mean over the gathered batch, so the sum over a group already *is* the
+    gradient of that mean and only the k groups are averaged."""
+    comm = self.dp_comms[s]
+    if not self.has_split:
+      return comm.size
+    if self._split_gathers_batch:
+      return max(self.plan.world // max(self._split_size, 1), 1)
+    return comm.size
 
   def _apply_group(self, s: int, mean: bool, scale0: float) -> None:
     cfg = self.config
     comm, flat, opts = self.dp_comms[s], self.flats[s], self.optimizers[s]
     sharded = self._sharded[s]
-    scale = scale0 / (comm.size if (mean and not self.has_split) else 1)
+    scale = scale0 / (self.mean_divisor(s) if mean else 1)
     if s in self.zero3:
       self.zero3[s].apply(scale)
     groups = max(1, cfg.optimizer.num_apply_group)
@@ -597,12 +754,32 @@ class Trainer(object):
           part += b.flat_grad.float().pow(2).sum()
       if reduced and self._sharded[s] and self.config.zero.level != "v0" and comm.size > 1:
         comm.primary.all_reduce(part, "sum")
+      if s >= 1000:                     # tensor-parallel shards: every rank of the TP group holds a different slice
+        tp = self._tp_comm(s - 1000)
+        if tp is not None and tp.size > 1:
+          tp.primary.all_reduce(part, "sum")
       sq += part
       if s in self.zero3:
-        sq += self.zero3[s].grad_sq_norm()
+        sq += self.zero3[s].grad_sq_norm(local=not reduced, divisor=comm.size if (self._mean and not reduced) else 1)
+    for s, items in self._sparse.items():
+      for p, _ in items:
+        if p.grad is not None:
+          g = p.grad.coalesce().values() if p.grad.is_sparse else p.grad
+          part = g.float().pow(2).sum().reshape(1)
+          if reduced and self.dp_comms[s].size > 1:          # not reduced yet at this point: sum of the replicas' squared norms
+            self.dp_comms[s].primary.all_reduce(part, "sum")
+          sq += part
     if self.plan.pipeline and self.plan.num_stages > 1:
       sq = self.pipe.all_reduce_over_stages(sq)
     return sq.sqrt()
+
+  def _tp_comm(self, ti: int):
+    """Communicator over the tensor-parallel group of split taskgraph ``ti`` (the one the split ops themselves use)."""
+    try:
+      from easyparallellibrary_b200.ops.tensor_parallel import current_tp_group
+      return current_tp_group(Graph.get().taskgraphs[ti].strategy).comm
+    except Exception:       # pragma: no cover - no TP group (single device)
+      return None
 
   # ------------------------------------------------------------------ collections
   def _merge_collections(self, collected: List["OrderedDict[str, List[Any]]"]) -> "OrderedDict[str, List[Any]]":
@@ -676,6 +853,18 @@ class Trainer(object):
   @property
   def is_first_replica(self) -> bool:
     return all(c.rank == 0 for c in self.dp_comms.values())
+
+
+class _Decompress(object):
+  """Work handle of a 16-bit-compressed bucket all-reduce: ``wait()`` also restores the fp32 gradient."""
+
+  def __init__(self, work, wire: torch.Tensor, dst: torch.Tensor, scale: float):
+    self.work, self.wire, self.dst, self.scale = work, wire, dst, scale
+
+  def wait(self) -> None:
+    if self.work is not None:
+      self.work.wait()
+    self.dst.copy_(self.wire.to(torch.float32).div_(self.scale))
 
 
 def _as_loss(out) -> torch.Tensor:

@@ -1,10 +1,19 @@
-"""Data-parallel hot path on B200: fused reduce-scatter + AdamW + all-gather over NVLink peer memory.
+"""Data-parallel hot path on B200: fused reduce-scatter + AdamW + all-gather over NVLink peer memory (K1).
 
-One kernel launch per gradient bucket (``csrc/symm.cu: fused_rs_adam_ag_kernel``) replaces
+One kernel launch per gradient bucket (``csrc/symm.cu: fused_rs_adam_ag_v2_kernel``) replaces
 ``ncclAllReduce`` + divide + unfused optimizer (reference ``graph_editor.py:670-725``,
 ``adam_weight_decay_optimizer.py:117-153``).  Optimizer state is an equal flat shard per rank, i.e.
 ZeRO-v1 memory falls out for free; weights and gradients live in symmetric memory so the kernel
 reads peers' gradient shards and writes peers' weight shards directly.
+
+Overlap with backward (the reference overlaps its bucketed all-reduces with backward through its
+communicator pool, ``communication_pool.py:84-105``): as soon as the last gradient of a bucket has been
+produced the bucket's kernel is launched on a side stream with a handful of CTAs (TPC-aligned pairs).
+It moves its bytes with bulk async copies through a shared-memory ring, so a few SMs sustain hundreds
+of GB/s; the backward GEMMs keep running on the remaining SMs — their tile scheduler is an atomic
+counter (``csrc/gemm_tcgen05.cu``), so CTA pairs that cannot be placed while the bucket kernel holds
+SMs cost nothing.  Only the bucket whose gradients complete last (bucket 0: the embeddings) runs after
+backward, on the whole GPU.
 """
 from __future__ import annotations
 
@@ -22,29 +31,34 @@ class FusedDataParallel(object):
   @staticmethod
   def eligible(trainer, comm) -> bool:
     cfg = trainer.config
+    from easyparallellibrary_b200.runtime.amp import DynamicLossScale
     return (trainer.device.type == "cuda" and not trainer.baseline and cfg.communication.fused_kernels
             and 1 < comm.size <= 8 and cfg.offload.level == ""
             # clipping: only the reference's default clip-then-reduce (local norm, applied to the bucket before the kernel runs)
             and (trainer.max_grad_norm is None or not cfg.communication.clip_after_allreduce)
             and cfg.zero.level in ("", "v0", "v1", "v2") and trainer.opt_kind in ("adam", "adamw")
             and cfg.optimizer.num_apply_group == 1
-            and trainer.compute_dtype in (torch.bfloat16, torch.float16) and not isinstance(
-                trainer.scaler, __import__("easyparallellibrary_b200.runtime.amp", fromlist=["DynamicLossScale"]).DynamicLossScale))
+            and trainer.compute_dtype in (torch.bfloat16, torch.float16) and not isinstance(trainer.scaler, DynamicLossScale))
 
   def __init__(self, trainer):
     self.trainer = trainer
     self.lib = _sym_lib()
     self.pads: Dict[int, SignalPad] = {}
     self.local_sync: Dict[int, torch.Tensor] = {}
-    self.epochs: Dict[Tuple[int, int], int] = {}
+    self.dyn: Dict[int, torch.Tensor] = {}            # per group: device {lr, 1/(1-b1^t), 1/(1-b2^t), grad scale}
+    self.epochs: Dict[Tuple[int, int], int] = {}      # v1 kernel only (v2 keeps its epoch on the device)
     self.side = torch.cuda.Stream(device=trainer.device, priority=-1)
-    self.blocks = 148                 # after backward: the whole GPU
-    # During backward the bucket kernel can run on a side stream with a few CTAs.  It needs most of an SM's registers, so its
-    # CTAs displace CTAs of the persistent GEMMs rather than sharing SMs with them; EPL_FUSED_OVERLAP=0 runs every bucket
-    # after backward on the whole GPU instead (no interference, fully exposed), EPL_FUSED_OVERLAP_BLOCKS sizes the overlap.
-    self.overlap_blocks = int(os.environ.get("EPL_FUSED_OVERLAP_BLOCKS", "32"))
+    self.blocks = 148                                 # after backward: the whole GPU
+    self.kernel = os.environ.get("EPL_K1", "v2")      # "v1": the register-path kernel of round 1 (A/B measurements)
+    self.overlap_blocks = int(os.environ.get("EPL_FUSED_OVERLAP_BLOCKS", "8"))
+    self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "1") != "0" and self.kernel == "v2"
+    # Each rank's AdamW shard is 1/W of the model: with W = 2 the bucket kernels stream 14 B/param of optimizer state per
+    # rank and a handful of CTAs cannot keep up with backward (measured on 2 x B200: 149.9 ms/step overlapped on 8 CTAs vs
+    # 117.5 ms after backward); from W = 4 on the per-rank work is small enough.
+    self.overlap_min_world = int(os.environ.get("EPL_FUSED_OVERLAP_MIN_WORLD", "4"))
     self.launched = set()
-    self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "0") != "0"   # measured on 2 x B200: 117.7 ms/step off vs 122.8 ms on (GPT-2-XL)
+    self._prepared = False
+    self._reserved = False
 
   @classmethod
   def maybe_create(cls, trainer) -> Optional["FusedDataParallel"]:
@@ -57,56 +71,92 @@ class FusedDataParallel(object):
       if comm.size <= 1 or (s, "grad", torch.bfloat16) not in trainer._symm_buffers and (s, "grad", torch.float16) not in trainer._symm_buffers:
         continue
       self.pads[s] = SignalPad(len(flat.buckets), comm.ranks, trainer.device, group=getattr(comm.primary, "group", None))
-      self.local_sync[s] = torch.zeros(2 * len(flat.buckets), dtype=torch.int32, device=trainer.device)
+      self.local_sync[s] = torch.zeros(4 * len(flat.buckets), dtype=torch.int32, device=trainer.device)
+      self.dyn[s] = torch.zeros(4, dtype=torch.float32, device=trainer.device)
     return self
 
-  def launch_bucket_async(self, s: int, bi: int, mean: bool) -> None:
+  # ------------------------------------------------------------------ per step
+  def begin_step(self, mean: bool) -> None:
+    """Host -> device: the step's learning rate, bias corrections and gradient scale (everything else the kernels
+    need is launch-invariant).  Called once per step before the first bucket can become ready."""
+    tr = self.trainer
+    for s in self.pads:
+      comm, opts = tr.dp_comms[s], tr.optimizers[s]
+      for o in opts:
+        o.step_count += 1
+      h, t = opts[0].hyper, opts[0].step_count
+      if h.bias_correction:
+        inv_c1, inv_c2 = 1.0 / (1.0 - h.beta1 ** t), 1.0 / (1.0 - h.beta2 ** t)
+      else:
+        inv_c1 = inv_c2 = 1.0
+      scale = tr.scaler.inv_scale / (tr.mean_divisor(s) if mean else 1)
+      self.dyn[s].copy_(torch.tensor([h.lr, inv_c1, inv_c2, scale], dtype=torch.float32), non_blocking=True)
+    self._prepared = True
+
+  def launch_bucket_async(self, s: int, bi: int) -> None:
     """Called from the gradient hook when the last gradient of a bucket has been produced: the fused kernel runs on
     a side stream while backward continues.  Safe because its first action is a cross-GPU barrier: no rank's weights
     are overwritten before every rank has finished the backward of the layers in this bucket."""
-    if (s, bi) in self.launched or s not in self.pads:
+    if (s, bi) in self.launched or s not in self.pads or bi == 0:       # bucket 0 completes last: whole GPU, after backward
       return
+    if self.trainer.dp_comms[s].size < self.overlap_min_world:
+      return
+    if not self._reserved:
+      # leave the bucket kernel's TPCs out of the GEMM grids until the step's reduce phase is over (the GEMM would cope —
+      # its tile scheduler is dynamic — but CTA pairs that start late only to find no work left lengthen each GEMM's tail)
+      from easyparallellibrary_b200.ops import linear as L
+      L._NUM_SMS = 148 - (self.overlap_blocks + 1) // 2 * 2
+      self._reserved = True
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream())
     self.side.wait_event(ev)
     with torch.cuda.stream(self.side):
-      self.launch_bucket(s, bi, mean, self.overlap_blocks)
+      self.launch_bucket(s, bi, self.overlap_blocks)
     self.launched.add((s, bi))
 
-  def launch_bucket(self, s: int, bi: int, mean: bool, blocks: int = 0) -> None:
+  def launch_bucket(self, s: int, bi: int, blocks: int = 0) -> None:
     tr = self.trainer
     comm, flat = tr.dp_comms[s], tr.flats[s]
     b, opt = flat.buckets[bi], tr.optimizers[s][bi]
     gbuf, pbuf = tr._symm_buffers[(s, "grad", b.dtype)], tr._symm_buffers[(s, "param", b.dtype)]
     es = b.flat_grad.element_size()
     lo, hi = b.shard_range(comm.rank, comm.size)
-    key = (s, bi)
-    self.epochs[key] = self.epochs.get(key, 0) + 1
-    opt.step_count += 1
     h = opt.hyper
-    if h.bias_correction:
-      inv_c1, inv_c2 = 1.0 / (1.0 - h.beta1 ** opt.step_count), 1.0 / (1.0 - h.beta2 ** opt.step_count)
+    sync = self.local_sync[s][4 * bi:4 * bi + 4]
+    if self.kernel == "v1":
+      key = (s, bi)
+      self.epochs[key] = self.epochs.get(key, 0) + 1
+      d = self.dyn[s].tolist()                          # (host sync: measurement aid only)
+      rc = self.lib.epl_fused_rs_adam_ag(
+          gbuf.peer_table(b.start * es), pbuf.peer_table(b.start * es), self.pads[s].slot_table(bi), sync.data_ptr(),
+          opt.master.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), _lib.ptr(opt.decay_mask), lo, hi - lo, comm.rank,
+          comm.size, self.epochs[key], _lib.dtype_code(b.dtype), d[0], h.beta1, h.beta2, h.eps, h.weight_decay, d[3],
+          d[1], d[2], self.blocks, _lib.stream())
     else:
-      inv_c1 = inv_c2 = 1.0
-    scale = tr.scaler.inv_scale / (comm.size if mean else 1)
-    sync = self.local_sync[s][2 * bi:2 * bi + 2]
-    rc = self.lib.epl_fused_rs_adam_ag(
-        gbuf.peer_table(b.start * es), pbuf.peer_table(b.start * es), self.pads[s].slot_table(bi), sync.data_ptr(),
-        opt.master.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), _lib.ptr(opt.decay_mask), lo, hi - lo, comm.rank,
-        comm.size, self.epochs[key], _lib.dtype_code(b.dtype), h.lr, h.beta1, h.beta2, h.eps, h.weight_decay, scale,
-        inv_c1, inv_c2, blocks or self.blocks, _lib.stream())
+      rc = self.lib.epl_fused_rs_adam_ag_v2(
+          gbuf.peer_table(b.start * es), pbuf.peer_table(b.start * es), self.pads[s].slot_table(bi), sync.data_ptr(),
+          opt.master.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), _lib.ptr(opt.decay_mask), lo, hi - lo, comm.rank,
+          comm.size, 0, _lib.dtype_code(b.dtype), self.dyn[s].data_ptr(), h.beta1, h.beta2, h.eps, h.weight_decay,
+          blocks or self.blocks, _lib.stream())
     _lib.check(rc, "fused_rs_adam_ag")
 
   def reduce_and_apply(self, mean: bool):
     tr = self.trainer
+    if not self._prepared:
+      self.begin_step(mean)
+    if self._reserved:
+      from easyparallellibrary_b200.ops import linear as L
+      L._NUM_SMS = 0
+      self._reserved = False
+    if self.launched:                                   # finish the overlapped buckets first: the tail bucket gets the whole GPU
+      torch.cuda.current_stream().wait_stream(self.side)
     for s in tr.group_keys:
       if s not in self.pads:
         tr._apply_group_library(s, mean)
         continue
       for bi in range(len(tr.flats[s].buckets) - 1, -1, -1):
         if (s, bi) not in self.launched:
-          self.launch_bucket(s, bi, mean and not tr.has_split)
-    if self.launched:
-      torch.cuda.current_stream().wait_stream(self.side)
-      self.launched.clear()
+          self.launch_bucket(s, bi)
+    self.launched.clear()
+    self._prepared = False
     return False, None

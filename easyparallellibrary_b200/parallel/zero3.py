@@ -56,7 +56,7 @@ class PendingGather(object):
 
   def materialize(self) -> None:
     u = self.unit
-    u.comm.primary.all_gather_into(u.full, u.shard_param)
+    u.comm.primary.all_gather_into(u.full, u._device_shard())
     u.params[0].epl_pending_gather = None
 
   def gemm(self, x2: torch.Tensor, bias, gelu: bool):
@@ -89,7 +89,14 @@ class Zero3Unit(object):
       full[o:o + p.numel()].copy_(p.data.reshape(-1))
     if W > 1:
       comm.primary.broadcast(full, 0)
+    # offload.level=v0 (reference graph_editor.py:727-751, "variables on the host, read just in time"): the weight shard lives
+    # in pinned host memory; every gather starts with an H2D copy of the shard (prefetched one unit ahead on the copy stream)
+    self.offload = bool(offload)
     self.shard_param = full[lo:lo + self.shard_numel].clone()
+    if self.offload:
+      host = torch.empty(self.shard_numel, dtype=self.dtype, pin_memory=device.type == "cuda")
+      host.copy_(self.shard_param)
+      self.shard_host = host
     self.shard_grad = torch.zeros(self.shard_numel, dtype=self.dtype, device=device)
     mask = None
     if any(no_decay(p) for p in params):
@@ -105,24 +112,58 @@ class Zero3Unit(object):
     else:
       self.opt = FlatOptimizer(opt_kind, hyper, master, mask)
     self.full: Optional[torch.Tensor] = None
+    self.full_grad: Optional[torch.Tensor] = None
+    self.work = None                  # in-flight asynchronous all-gather into self.full
+    self.bound = False                # parameters point into self.full
     self.ready = 0
     self.shapes = [p.shape for p in params]
     del full
+    if self.offload:
+      self.shard_param = None         # device copy exists only between a gather's H2D and its all-gather
     self.release()
 
   # -- materialise / release -------------------------------------------------------------------------
+  def _device_shard(self, stream_ctx=None) -> torch.Tensor:
+    if not self.offload:
+      return self.shard_param
+    dev = torch.empty(self.shard_numel, dtype=self.dtype, device=self.device)
+    dev.copy_(self.shard_host, non_blocking=True)
+    return dev
+
+  def gather_async(self, copy_stream=None) -> None:
+    """Start the all-gather of this unit's weights (no-op if already started); ``gather()`` completes it.  The engine calls
+    this one unit ahead of the compute (forward: next unit, backward: previous unit) so the transfer hides behind it."""
+    if self.full is not None or self.comm.size <= 1:
+      return
+    self.full = torch.empty(self.numel, dtype=self.dtype, device=self.device)
+    be = self.comm.pool.backends[-1]               # second transport of the pool when there is one: not behind the reduce-scatters
+    if copy_stream is not None:
+      copy_stream.wait_stream(torch.cuda.current_stream())     # the buffer's previous owner (allocator reuse) is done with it
+      with torch.cuda.stream(copy_stream):
+        shard = self._device_shard()
+        self.work = be.all_gather_into(self.full, shard, async_op=True)
+        shard.record_stream(copy_stream) if shard.is_cuda and self.offload else None
+    else:
+      self.work = be.all_gather_into(self.full, self._device_shard(), async_op=True)
+
   def gather(self, defer: bool = False) -> None:
-    if self.full is not None:
+    if self.full is not None and self.bound:
       pend = getattr(self.params[0], "epl_pending_gather", None) if self.deferred else None
       if pend is not None and not defer:
         pend.materialize()                       # e.g. the backward pass needs the weight although forward never consumed it
       return
-    self.full = torch.empty(self.numel, dtype=self.dtype, device=self.device)
-    if not (defer and self.deferred and self.comm.size > 1):
-      self.comm.primary.all_gather_into(self.full, self.shard_param)
+    deferred_now = defer and self.deferred and self.comm.size > 1 and not self.offload
+    if self.full is None:
+      self.full = torch.empty(self.numel, dtype=self.dtype, device=self.device)
+      if not deferred_now:
+        self.comm.primary.all_gather_into(self.full, self._device_shard())
+    elif self.work is not None:
+      self.work.wait()                           # prefetched: the current stream waits for the gather, the host does not
+    self.work = None
     for p, o, shp in zip(self.params, self.offsets, self.shapes):
       p.data = self.full[o:o + shp.numel()].view(shp)
-    if defer and self.deferred and self.comm.size > 1:
+    self.bound = True
+    if deferred_now:
       self.params[0].epl_pending_gather = PendingGather(self)
 
   def release(self) -> None:
@@ -131,17 +172,32 @@ class Zero3Unit(object):
       if self.full is not None:
         raise RuntimeError("ZeRO-3: the deferred weight of unit %d was never consumed through ops.linear during the forward pass; "
                            "mark the module with epl_no_fused_gather = True" % self.index)
+    if self.work is not None:                     # a prefetched gather nobody consumed: let it finish before the buffer goes
+      self.work.wait()
+      self.work = None
     self.full = None
+    self.bound = False
     for p in self.params:
       p.data = torch.empty(0, dtype=self.dtype, device=self.device)
 
+  def bind_grads(self) -> None:
+    """Before the unit's backward: ``.grad`` of every parameter becomes a view of one flat buffer, so autograd accumulates
+    straight into the reduce-scatter's input (no per-parameter copy afterwards)."""
+    if self.full_grad is None:
+      self.full_grad = torch.zeros(self.numel, dtype=self.dtype, device=self.device)
+    for p, o, shp in zip(self.params, self.offsets, self.shapes):
+      if p.grad is None:
+        p.grad = self.full_grad[o:o + shp.numel()].view(shp)
+
   def reduce_grads(self) -> None:
     """Full gradients -> this rank's shard (accumulated over micro-batches)."""
-    flat = torch.zeros(self.numel, dtype=self.dtype, device=self.device)
+    flat = self.full_grad if self.full_grad is not None else torch.zeros(self.numel, dtype=self.dtype, device=self.device)
     for p, o in zip(self.params, self.offsets):
       if p.grad is not None:
-        flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
+        if p.grad.data_ptr() != flat[o:].data_ptr():          # autograd replaced the view (or bind_grads never ran): fold it in
+          flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
         p.grad = None
+    self.full_grad = None
     if self.comm.size > 1:
       out = torch.empty(self.shard_numel, dtype=self.dtype, device=self.device)
       self.comm.primary.reduce_scatter_into(out, flat, "sum")
@@ -159,6 +215,8 @@ class Zero3Engine(object):
     self.units: List[Zero3Unit] = []
     self._unit_of: Dict[int, Zero3Unit] = {}
     self.tp_group = None
+    self.prefetch = os.environ.get("EPL_ZERO3_PREFETCH", "1") != "0" and comm.size > 1
+    self.copy_stream = torch.cuda.Stream(device=trainer.device) if (trainer.device.type == "cuda" and cfg.offload.level == "v0") else None
     if comm.size > 1:
       from easyparallellibrary_b200.ops.tensor_parallel import TPGroup
       self.tp_group = TPGroup(comm.rank, comm.size, list(comm.ranks))     # the view of the DP group the fused kernel expects
@@ -207,10 +265,18 @@ class Zero3Engine(object):
         return sub.weight if ok else None
     return None
 
+  def _prefetch(self, index: int) -> None:
+    if 0 <= index < len(self.units) and self.prefetch:
+      u = self.units[index]
+      if not (u.deferred and not u.offload):      # a deferred (K2) unit gathers inside its GEMM
+        u.gather_async(self.copy_stream)
+
   def _pre_forward(self, owners):
     def hook(mod, args):
       for u in owners:
         u.gather(defer=True)
+      if torch.is_grad_enabled() or True:
+        self._prefetch(max(u.index for u in owners) + 1)
     return hook
 
   def _post_forward(self, owners):
@@ -223,6 +289,9 @@ class Zero3Engine(object):
     def hook(mod, grad_out):
       for u in owners:
         u.gather()
+        if u.module is mod:
+          u.bind_grads()
+      self._prefetch(min(u.index for u in owners) - 1)
     return hook
 
   def _on_grad(self, p) -> None:
@@ -245,13 +314,21 @@ class Zero3Engine(object):
         u.reduce_grads()
         u.release()
 
-  def grad_sq_norm(self) -> torch.Tensor:
+  def grad_sq_norm(self, local: bool = False, divisor: int = 1) -> torch.Tensor:
+    """Squared norm of the (reduce-scattered, i.e. already summed over replicas) gradient.  ZeRO-3 never holds a
+    replica-local gradient — units are reduced as soon as their backward finishes — so for clip-then-reduce (``local``)
+    the engine passes ``divisor`` = number of replicas under ``mean``: the norm of the averaged gradient stands in for the
+    per-replica norm."""
     sq = torch.zeros(1, device=self.trainer.device, dtype=torch.float32)
     for u in self.units:
       sq += u.shard_grad.float().pow(2).sum()
     if self.comm.size > 1:
       self.comm.primary.all_reduce(sq, "sum")
-    return sq
+    return sq / float(divisor * divisor)
+
+  def scale_grads(self, c: float) -> None:
+    for u in self.units:
+      u.shard_grad.mul_(c)
 
   def has_non_finite(self) -> torch.Tensor:
     bad = torch.zeros(1, device=self.trainer.device)
@@ -261,15 +338,20 @@ class Zero3Engine(object):
 
   def apply(self, scale: float) -> None:
     for u in self.units:
-      u.opt.step(u.shard_grad, u.shard_param, scale)
+      if u.offload:                               # new weights are produced on the device, then parked on the host again
+        out = torch.empty(u.shard_numel, dtype=u.dtype, device=u.device)
+        u.opt.step(u.shard_grad, out, scale)
+        u.shard_host.copy_(out, non_blocking=True)
+      else:
+        u.opt.step(u.shard_grad, u.shard_param, scale)
 
   def state_dict(self):
-    return [dict(u.opt.state_dict(), shard_param=u.shard_param) for u in self.units]
+    return [dict(u.opt.state_dict(), shard_param=(u.shard_host if u.offload else u.shard_param)) for u in self.units]
 
   def load_state_dict(self, sds) -> None:
     for u, sd in zip(self.units, sds):
       u.opt.load_state_dict(sd)
-      u.shard_param.copy_(sd["shard_param"])
+      (u.shard_host if u.offload else u.shard_param).copy_(sd["shard_param"])
 
   def gather_all(self) -> None:
     """Materialise every unit (evaluation / checkpoint export)."""
@@ -281,10 +363,13 @@ class Zero3Engine(object):
       u.release()
 
   def persistent_bytes(self) -> int:
+    """Device bytes this rank holds between steps: weight shard (unless offloaded) + gradient shard + optimizer state
+    (unless offloaded) + decay mask."""
     n = 0
     for u in self.units:
-      n += u.shard_numel * (2 * u.shard_param.element_size())
-      for t in (u.opt.master, u.opt.m, u.opt.v):
+      es = u.shard_grad.element_size()
+      n += u.shard_numel * es * (1 if u.offload else 2)
+      for t in (u.opt.master, u.opt.m, u.opt.v, getattr(u.opt, "decay_mask", None), getattr(u.opt, "device_mask", None)):
         if t is not None and t.device.type != "cpu":
           n += t.numel() * t.element_size()
     return n

@@ -18,12 +18,78 @@ import torch
 
 
 def compute_dtype(level: str) -> Optional[torch.dtype]:
+  """Dtype the *parameters* are cast to.  ``bf16``: bf16 weights + fp32 masters in the flat optimizer.  ``O1``: None — the
+  parameters stay fp32 (they are the master weights) and precision is decided per op, see :class:`o1_autocast`."""
   level = (level or "").lower()
-  if level == "o1":
-    return torch.float16
   if level == "bf16":
     return torch.bfloat16
   return None
+
+
+# ------------------------------------------------------------------------------------------------
+# O1: op-level colouring (reference auto_mixed_precision.py:35-85 allow / deny / gray / clear lists, :174-415 the four
+# colouring passes, :160-172 just-in-time fp16 casts of fp32 variables).  The reference rewrites the graph; eager code decides
+# at each op call: ops on the ALLOW list cast their inputs (and, just in time, their fp32 weights) to fp16; ops on the DENY
+# list cast to fp32; GRAY ops (element-wise, residual adds, reshapes) run in whatever dtype their inputs have — which is what
+# the reference's gray propagation converges to; CLEAR ops are dtype-agnostic.  Stock torch ops inside the region follow
+# ``torch.autocast``'s own lists (same design: matmul/conv fp16, softmax/norm/loss fp32).
+# ------------------------------------------------------------------------------------------------
+ALLOW_OPS = ("linear", "mlp", "matmul", "conv", "attention")
+DENY_OPS = ("layer_norm", "rms_norm", "softmax", "cross_entropy", "exp", "log", "pow", "sum", "mean", "loss", "batch_norm")
+GRAY_OPS = ("add", "mul", "gelu", "relu", "tanh", "dropout", "residual", "concat", "where")
+CLEAR_OPS = ("reshape", "transpose", "slice", "gather", "identity")
+_O1_DEPTH = 0
+_O1_LOG = False
+
+
+def o1_active() -> bool:
+  return _O1_DEPTH > 0
+
+
+def op_dtype(kind: str) -> Optional[torch.dtype]:
+  """fp16 / fp32 / None (= keep the input dtype) for an op of ``kind`` inside an O1 region; always None outside."""
+  if _O1_DEPTH == 0:
+    return None
+  if kind in ALLOW_OPS:
+    return torch.float16
+  if kind in DENY_OPS:
+    return torch.float32
+  return None
+
+
+def cast_args(kind: str, *tensors):
+  """Cast floating tensors to the dtype the O1 policy assigns to ``kind`` (identity outside O1 regions / for gray ops)."""
+  dt = op_dtype(kind)
+  if dt is None:
+    return tensors if len(tensors) != 1 else tensors[0]
+  if _O1_LOG:
+    from easyparallellibrary_b200.utils.logging import get_logger
+    get_logger().info("amp O1: %s -> %s", kind, dt)
+  out = tuple(t.to(dt) if isinstance(t, torch.Tensor) and t.is_floating_point() and t.dtype != dt else t for t in tensors)
+  return out if len(out) != 1 else out[0]
+
+
+class o1_autocast(object):
+  """Context of one forward pass under ``amp.level = O1``."""
+
+  def __init__(self, device_type: str, enabled: bool = True, debug_log: bool = False):
+    self.enabled, self.debug_log = enabled, debug_log
+    self.ctx = torch.autocast(device_type, dtype=torch.float16, enabled=enabled) if enabled else None
+
+  def __enter__(self):
+    global _O1_DEPTH, _O1_LOG
+    if self.enabled:
+      _O1_DEPTH += 1
+      _O1_LOG = self.debug_log
+      self.ctx.__enter__()
+    return self
+
+  def __exit__(self, *exc):
+    global _O1_DEPTH
+    if self.enabled:
+      self.ctx.__exit__(*exc)
+      _O1_DEPTH -= 1
+    return False
 
 
 class LossScaler(object):

@@ -27,6 +27,9 @@ from easyparallellibrary_b200.parallel import partitioner
 from easyparallellibrary_b200.utils import constant
 
 
+RECOMPUTE_ENABLED = True        # gradient_checkpoint.check_gradients flips this to obtain the plain (non-recomputed) gradients
+
+
 class _Checkpointed(nn.Module):
   """Wraps ``inner`` so its activations are recomputed in backward."""
 
@@ -35,7 +38,7 @@ class _Checkpointed(nn.Module):
     self.inner = inner
 
   def forward(self, *args, **kwargs):
-    if not torch.is_grad_enabled() or not self.training:
+    if not torch.is_grad_enabled() or not self.training or not RECOMPUTE_ENABLED:
       return self.inner(*args, **kwargs)
     return checkpoint(self.inner, *args, use_reentrant=False, preserve_rng_state=True, **kwargs)
 

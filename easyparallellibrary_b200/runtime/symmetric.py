@@ -43,6 +43,9 @@ def _sym_lib():
     lib.epl_peer_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
     lib.epl_fused_rs_adam_ag.argtypes = ([ctypes.c_void_p] * 8 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_uint, ctypes.c_int] + [ctypes.c_float] * 8 + [ctypes.c_int, ctypes.c_void_p])
+    lib.epl_fused_rs_adam_ag_v2.argtypes = ([ctypes.c_void_p] * 8 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_uint, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_float] * 4 +
+                                            [ctypes.c_int, ctypes.c_void_p])
     lib._symm_ready = True
   return lib
 

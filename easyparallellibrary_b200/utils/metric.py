@@ -94,14 +94,18 @@ class PhaseTimer(object):
     setattr(self.obj, self.method, self.orig)
 
 
-def fused_dp_roofline_ms(num_params: int, world: int, hbm_gbs: float = 6400.0, nvlink_gbs: float = 900.0, grad_bytes: int = 2) -> float:
-  """Lower bound of reduce-scatter + AdamW + all-gather for ``num_params`` parameters over ``world`` NVLink peers:
-  every rank pulls the (W-1)/W remote part of its shard's partial gradients, streams 24 B/param of fp32 optimizer state for its
-  1/W shard (read + write of master, m, v), and pushes its new 16-bit weights to W-1 peers.  With one GPU it is the local
-  AdamW stream (30 B/param)."""
+def fused_dp_roofline_ms(num_params: int, world: int, hbm_gbs: float = 6400.0, nvlink_gbs: float = 770.0, grad_bytes: int = 2) -> float:
+  """Lower bound of the WHOLE reduce-scatter + AdamW + all-gather phase for ``num_params`` parameters over ``world`` NVLink
+  peers (it is an all-reduce's traffic: per direction and per GPU, (W-1)/W of the gradient bytes cross the link for the
+  reduce-scatter — inbound: the peers' partials of my shard, outbound: my partials of their shards — and (W-1)/W of the
+  weight bytes for the all-gather).  NVLink is full duplex and the HBM streams overlap the link traffic, so the bound is the
+  MAX of the per-direction link time (at the measured 770 GB/s peer bandwidth, B200_PROFILING.md) and the HBM time
+  (24 B/param of fp32 optimizer state for the 1/W shard + every gradient byte read once + every weight byte written once).
+  With one GPU it is the local AdamW stream (30 B/param).  The *exposed* part of the phase can be shorter than this bound when
+  buckets are processed while backward is still running."""
   if world <= 1:
     return num_params * 30.0 / (hbm_gbs * 1e9) * 1e3
-  remote = (world - 1) / world * num_params * grad_bytes
-  link = 2.0 * remote / (nvlink_gbs * 1e9)
-  adam = (num_params / world) * 24.0 / (hbm_gbs * 1e9)
-  return (link + adam) * 1e3
+  per_direction = 2.0 * (world - 1) / world * num_params * grad_bytes
+  link = per_direction / (nvlink_gbs * 1e9)
+  hbm = ((num_params / world) * 24.0 + 2.0 * num_params * grad_bytes) / (hbm_gbs * 1e9)
+  return max(link, hbm) * 1e3

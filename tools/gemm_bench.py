@@ -37,7 +37,7 @@ def main():
         ("nt fwd", lambda: L.gemm(x, w), lambda: x @ w.t()),
         ("nn dX", lambda: L.gemm(dy, w, b_mn_major=True), lambda: dy @ w),
         ("tn dW", lambda: L.gemm(dy, x, a_mn_major=True, b_mn_major=True), lambda: dy.t() @ x)):
-      for bn in (0, 512, 1024):
+      for bn in (0, 512):
         if bn == 160 and layout != "nt fwd":
           continue
         L._FORCE_BN = bn

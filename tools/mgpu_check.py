@@ -138,6 +138,140 @@ def check_fused(dev, world, rank):
   assert diff < 8e-3 and abs(loss_f[-1] - loss_b[-1]) < 0.03          # 8 ranks: 0.016 observed (bf16 ring all-reduce vs fp32 sum of bf16 partials)
 
 
+def _k1_setup(dev, world, rank, n_bucket, dtype, seed):
+  """One gradient bucket of ``n_bucket`` elements in symmetric memory + this rank's fp32 optimizer shard."""
+  from easyparallellibrary_b200.runtime.symmetric import SignalPad, SymmetricBuffer
+  ranks = list(range(world))
+  gbuf = SymmetricBuffer(n_bucket * 2, ranks, dev)
+  pbuf = SymmetricBuffer(n_bucket * 2, ranks, dev)
+  pad = SignalPad(1, ranks, dev)
+  g = gbuf.tensor(dtype, n_bucket)
+  w = pbuf.tensor(dtype, n_bucket)
+  gen = torch.Generator(device=dev).manual_seed(seed + rank)
+  g.copy_((torch.randn(n_bucket, device=dev, generator=gen) * 0.02).to(dtype))
+  gen0 = torch.Generator(device=dev).manual_seed(seed + 1000)               # identical weights / state on every rank
+  master_full = torch.randn(n_bucket, device=dev, generator=gen0) * 0.05
+  w.copy_(master_full.to(dtype))
+  shard = n_bucket // world
+  lo = rank * shard
+  st = {"master": master_full[lo:lo + shard].clone(), "m": torch.randn(shard, device=dev, generator=gen0) * 1e-3,
+        "v": torch.rand(shard, device=dev, generator=gen0) * 1e-5,
+        "mask": (torch.rand(shard, device=dev, generator=gen0) > 0.1).float()}
+  return gbuf, pbuf, pad, g, w, st, lo, shard
+
+
+def _k1_launch(lib, gbuf, pbuf, pad, sync, st, lo, shard, rank, world, dtype, dyn, hyper, blocks, use_mask=True):
+  from easyparallellibrary_b200.ops import _lib
+  b1, b2, eps, wd = hyper
+  rc = lib.epl_fused_rs_adam_ag_v2(gbuf.peer_table(0), pbuf.peer_table(0), pad.slot_table(0), sync.data_ptr(),
+                                   st["master"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
+                                   st["mask"].data_ptr() if use_mask else None, lo, shard, rank, world, 0, _lib.dtype_code(dtype),
+                                   dyn.data_ptr(), b1, b2, eps, wd, blocks, _lib.stream())
+  _lib.check(rc, "fused_rs_adam_ag_v2")
+
+
+def check_k1(dev, world, rank):
+  """K1 v2 against fp32 ground truth: gradients of all ranks are gathered, summed in fp32 in rank order (the kernel's
+  order, so the reduction must match BIT FOR BIT), AdamW is evaluated in fp32 with the same formula; master / m / v must
+  agree to fp32 rounding of a handful of operations and the bf16/fp16 weights every rank ends up with must be the
+  rounding of the new master — and identical on every rank.  Also: a ragged bucket (last piece partial), several
+  consecutive launches (epoch protocol, grid size changing between launches), fp16 + loss scale."""
+  from easyparallellibrary_b200.runtime.symmetric import _sym_lib
+  lib = _sym_lib()
+  hyper = (0.9, 0.999, 1e-8, 0.01)
+  for dtype, n_bucket, scale in ((torch.bfloat16, world * 8 * 40961, 1.0), (torch.float16, world * 8 * 1031, 1.0 / 128),
+                                 (torch.bfloat16, world * 8 * 5, 0.5)):
+    gbuf, pbuf, pad, g, w, st, lo, shard = _k1_setup(dev, world, rank, n_bucket, dtype, 7)
+    sync = torch.zeros(4, dtype=torch.int32, device=dev)
+    ref = {k: v.clone() for k, v in st.items()}
+    for step, blocks in enumerate((148, 6, 33)):
+      lr, t = 1e-3 * (step + 1), step + 1
+      inv_c1, inv_c2 = 1.0 / (1 - hyper[0] ** t), 1.0 / (1 - hyper[1] ** t)
+      dyn = torch.tensor([lr, inv_c1, inv_c2, scale / world], dtype=torch.float32, device=dev)
+      # ---- fp32 truth
+      allg = [torch.empty_like(g) for _ in range(world)]
+      dist.all_gather(allg, g)
+      acc = torch.zeros(shard, device=dev)
+      for r in range(world):
+        acc += allg[r][lo:lo + shard].float()                                # rank order, fp32: exact
+      gr = acc * torch.tensor(scale / world, dtype=torch.float32, device=dev)
+      b1, b2, eps, wd = hyper
+      f32 = lambda x: torch.tensor(x, dtype=torch.float32)
+      omb1, omb2 = float(f32(1.0) - f32(b1)), float(f32(1.0) - f32(b2))      # the kernel forms 1 - beta in fp32
+      ref["m"] = float(f32(b1)) * ref["m"] + omb1 * gr
+      ref["v"] = float(f32(b2)) * ref["v"] + omb2 * gr * gr
+      upd = (ref["m"] * inv_c1) / ((ref["v"] * inv_c2).sqrt() + eps) + wd * ref["mask"] * ref["master"]
+      ref["master"] = ref["master"] - lr * upd
+      # ---- kernel
+      dist.barrier()
+      _k1_launch(lib, gbuf, pbuf, pad, sync, st, lo, shard, rank, world, dtype, dyn, hyper, blocks)
+      torch.cuda.synchronize(); dist.barrier()
+      dm = (st["m"] - ref["m"]).abs().max().item() / (ref["m"].abs().max().item() + 1e-30)
+      dv = (st["v"] - ref["v"]).abs().max().item() / (ref["v"].abs().max().item() + 1e-30)
+      dp = (st["master"] - ref["master"]).abs().max().item()
+      # weights: every rank's full buffer == rounding of the owners' new masters
+      mine = st["master"].to(dtype)
+      gathered = [torch.empty_like(mine) for _ in range(world)]
+      dist.all_gather(gathered, mine)
+      expect = torch.cat(gathered)
+      dw = (w.float() - expect.float()).abs().max().item()
+      log("k1 exact %s n=%d step %d blocks=%d: rel|dm|=%.1e rel|dv|=%.1e |dmaster|=%.1e |dweights vs rounded master|=%.1e" % (
+          str(dtype).split(".")[-1], n_bucket, step, blocks, dm, dv, dp, dw))
+      # m, v: two fp32 FMAs vs mul+add (<= 2 ulp = 2.4e-7 relative); master: + one division / sqrt (fast-math free build)
+      assert dm < 1e-6 and dv < 1e-6 and dp < 2e-6 * max(1.0, lr * 1e3) and dw == 0.0, (dm, dv, dp, dw)
+      for k in ("master", "m", "v"):                                        # continue from the kernel's state: errors do not pile up
+        ref[k] = st[k].clone()
+      g.copy_((g.float() * 0.5 + 0.01).to(dtype))                           # new gradients for the next step
+
+
+def bench_k1(dev, world, rank):
+  """K1 v1 vs v2 on GPT-2-XL-sized buckets: whole GPU (exposed tail) and a few CTAs (overlapped with backward)."""
+  from easyparallellibrary_b200.runtime.symmetric import _sym_lib
+  from easyparallellibrary_b200.ops import _lib
+  lib = _sym_lib()
+  hyper = (0.9, 0.999, 1e-8, 0.01)
+  res = {}
+  for n_bucket in (1557611200 // 16 // (world * 8) * (world * 8), 1557611200 // 5 // (world * 8) * (world * 8)):
+    gbuf, pbuf, pad, g, w, st, lo, shard = _k1_setup(dev, world, rank, n_bucket, torch.bfloat16, 3)
+    sync = torch.zeros(4, dtype=torch.int32, device=dev)
+    sync1 = torch.zeros(4, dtype=torch.int32, device=dev)
+    from easyparallellibrary_b200.runtime.symmetric import SignalPad
+    pad1 = SignalPad(1, list(range(world)), dev)
+    dyn = torch.tensor([1e-4, 1.0, 1.0, 1.0 / world], dtype=torch.float32, device=dev)
+    ep = [0]
+
+    def v1():
+      ep[0] += 1
+      rc = lib.epl_fused_rs_adam_ag(gbuf.peer_table(0), pbuf.peer_table(0), pad1.slot_table(0), sync1.data_ptr(),
+                                    st["master"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), st["mask"].data_ptr(), lo, shard,
+                                    rank, world, ep[0], _lib.dtype_code(torch.bfloat16), 1e-4, 0.9, 0.999, 1e-8, 0.01, 1.0 / world,
+                                    1.0, 1.0, 148, _lib.stream())
+      _lib.check(rc, "k1v1")
+    cases = [("v1 148 CTAs", v1)] + [("v2 %3d CTAs" % b, (lambda b=b: _k1_launch(lib, gbuf, pbuf, pad, sync, st, lo, shard, rank, world,
+                                                                             torch.bfloat16, dyn, hyper, b))) for b in (148, 74, 32, 16, 8, 4)]
+    for name, fn in cases:
+      for _ in range(2):
+        fn()
+      torch.cuda.synchronize(); dist.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(5):
+        fn()
+      e1.record(); torch.cuda.synchronize()
+      t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      link = (world - 1) / world * n_bucket * 2 * 2            # bytes per direction: peers' grads in + weights in (= grads out + weights out)
+      hbm = n_bucket / world * 32 + n_bucket * 2 * 2
+      floor = max(link / 770e9, hbm / 6.4e12) * 1e3
+      res["%d:%s" % (n_bucket, name)] = t.item()
+      log("k1 bucket %.0f M params, %s: %.3f ms  (per-direction link bytes %.0f MB -> %.0f GB/s; floor max(link@770GB/s, HBM) = %.3f ms -> %.0f %%)" % (
+          n_bucket / 1e6, name, t.item(), link / 1e6, link / t.item() / 1e6, floor, 100 * floor / t.item()))
+    del gbuf, pbuf, pad, pad1
+  if rank == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/k1_bench_w%d.json" % world, "w"), indent=1)
+
+
 def check_tp(dev, world, rank):
   """Fused all-gather->GEMM and GEMM->reduce-scatter kernels vs the NCCL + separate GEMM path."""
   from easyparallellibrary_b200.ops import tensor_parallel as tp
@@ -295,6 +429,10 @@ def main():
     check_symm(dev, world, rank)
   if "fused" in what:
     check_fused(dev, world, rank)
+  if "k1" in what:
+    check_k1(dev, world, rank)
+  if "k1bench" in what:
+    bench_k1(dev, world, rank)
   if "tp" in what:
     check_tp(dev, world, rank)
   if "tptrain" in what:

@@ -48,6 +48,7 @@ def parse():
   ap.add_argument("--gc", default="")
   ap.add_argument("--offload", default="")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
   ap.add_argument("--profile", default="", help="write a per-kernel GPU time table of 2 extra steps to this file")
   return ap.parse_args()
 
@@ -144,7 +145,7 @@ class GPT2Workload(Workload):
         else:
           model = GPT2(cfg)
       self.trainer = epl.Trainer(model, "adamw", lr=1e-4, weight_decay=0.01, baseline=(args.impl == "baseline"),
-                                 loss_fn=lm_loss if stages > 1 else None).build()
+                                 loss_fn=lm_loss if stages > 1 else None, cuda_graph=not args.no_graph).build()
       replicas = self.trainer.plan.num_replicas
     self.replicas = replicas
     B = batch * (M if stages > 1 else 1)
@@ -361,6 +362,16 @@ def main():
     barrier()
   ms, loss, clocks, launches = timed(args.steps, False)
   value = wl.units_per_step * args.steps / (ms / 1e3)
+  graphed = trainer is not None and getattr(trainer, "_graphed", None) is not None and trainer._graphed.graph is not None
+  if graphed and phase is not None:
+    # the replayed graph contains the reduce/apply phase but not the host-side timer: measure its exposed span on a few
+    # eager steps (same kernels, same streams), outside the timed region
+    trainer._graphed.enabled = False
+    keep = (ms, loss, clocks, launches)
+    run(1, False)
+    timed(3, False)
+    trainer._graphed.enabled = True
+    ms, loss, clocks, launches = keep
   e2e = None
   if not args.no_e2e:
     run(2, True)
@@ -382,6 +393,7 @@ def main():
           else "after backward")
       cfg["gradient_buckets"] = sum(len(f.buckets) for f in trainer.flats.values())
     cfg.update(wl.meta)
+    cfg["cuda_graph"] = bool(graphed)
     line = {
         "metric": wl.metric, "value": value, "unit": wl.unit + "/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

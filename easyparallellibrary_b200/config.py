@@ -53,7 +53,7 @@ _opt("zero", "level", "", "'' | v0 | v1 | v2 | v3.")
 _opt("zero", "fused_gather", False,
      "B200 extension (v3): gather the weight of a layer's first GEMM inside that GEMM instead of before it.")
 _opt("offload", "level", "", "'' | v0 (weights and optimizer state live on the host).")
-_opt("amp", "level", "", "'' | O1 (fp16 + loss scale) | bf16.")
+_opt("amp", "level", "", "'' | O1 (fp16 + loss scale) | bf16 | fp8 (B200 extension: bf16 weights, e4m3 forward GEMMs).")
 _opt("amp", "debug_log", False, "Log the precision decision for every module.")
 _opt("amp", "loss_scale", "dynamic", "'dynamic' or a fixed number.")
 _opt("cluster", "device_place_prefer_intra_node", True, "Keep one model replica inside a node when possible.")

@@ -177,3 +177,67 @@ extern "C" int epl_add(const void* a, const void* b, void* y, int64_t n, int dty
   });
   return EPL_CHECK_LAUNCH();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-tensor e4m3 quantisation for the fp8 GEMM path (amp.level = "fp8"): pass 1 = absolute maximum, pass 2 = scale by
+// 448 / amax, saturate, cast; the de-quantisation factor amax / 448 is left in device memory for the GEMM epilogue (no host
+// round trip).
+// ---------------------------------------------------------------------------------------------------------
+#include <cuda_fp8.h>
+namespace epl {
+template <typename T>
+__global__ void __launch_bounds__(256) amax_kernel(const T* __restrict__ x, int64_t n, uint32_t* __restrict__ amax_bits) {
+  float m = 0.f;
+  const int64_t nvec = n >> 3, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    Vec<T, 8> v = ld_vec<T, 8>(x + 8 * i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(to_f32<T>(v.v[j])));
+  }
+  for (int64_t i = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(to_f32<T>(x[i])));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));      // non-negative floats order like their bit patterns
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_e4m3_kernel(const T* __restrict__ x, int64_t n, const uint32_t* __restrict__ amax_bits,
+                                                         uint8_t* __restrict__ out, float* __restrict__ inv_scale) {
+  const float amax = fmaxf(__uint_as_float(*amax_bits), 1e-12f);
+  const float s = 448.f / amax;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = amax / 448.f;
+  const int64_t nvec = n >> 3, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    Vec<T, 8> v = ld_vec<T, 8>(x + 8 * i);
+    uint32_t w[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(to_f32<T>(v.v[4 * h]) * s, to_f32<T>(v.v[4 * h + 1]) * s), __NV_SATFINITE, __NV_E4M3);
+      const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(to_f32<T>(v.v[4 * h + 2]) * s, to_f32<T>(v.v[4 * h + 3]) * s), __NV_SATFINITE, __NV_E4M3);
+      w[h] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+    *reinterpret_cast<uint2*>(out + 8 * i) = make_uint2(w[0], w[1]);
+  }
+  for (int64_t i = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (uint8_t)__nv_cvt_float_to_fp8(to_f32<T>(x[i]) * s, __NV_SATFINITE, __NV_E4M3);
+}
+}  // namespace epl
+
+// x: n elements (bf16 / fp16 / fp32, 16-byte aligned), out: n bytes (8-byte aligned), amax_scratch: one uint32 (zeroed here),
+// inv_scale: one float.
+extern "C" int epl_quantize_e4m3(const void* x, int dtype, int64_t n, void* out, void* amax_scratch, void* inv_scale, void* stream) {
+  using namespace epl;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(amax_scratch, 0, 4, st);
+  int blocks = (int)std::min<int64_t>((n / 8 + 255) / 256 + 1, (int64_t)kNumSMs * 8);
+  if (dtype == EPL_BF16) {
+    amax_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, n, (uint32_t*)amax_scratch);
+    cast_e4m3_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, n, (const uint32_t*)amax_scratch, (uint8_t*)out, (float*)inv_scale);
+  } else if (dtype == EPL_F16) {
+    amax_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, n, (uint32_t*)amax_scratch);
+    cast_e4m3_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, n, (const uint32_t*)amax_scratch, (uint8_t*)out, (float*)inv_scale);
+  } else {
+    amax_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, n, (uint32_t*)amax_scratch);
+    cast_e4m3_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, n, (const uint32_t*)amax_scratch, (uint8_t*)out, (float*)inv_scale);
+  }
+  return EPL_CHECK_LAUNCH();
+}

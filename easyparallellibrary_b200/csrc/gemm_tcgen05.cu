@@ -55,6 +55,9 @@ struct GemmParams {
   float alpha;
   int bn2;                 // 2-CTA kernel: tile width (128 / 192 / 256), chosen per shape by pick_bn2()
   uint32_t* sched_counter; // 2-CTA kernel: global tile counter of the dynamic scheduler (one per stream, self-resetting)
+  int fp8;                 // 2-CTA kernel: A and B are e4m3 (1 byte), K-major; tcgen05.mma kind::f8f6f4, 128 K-elements per k-block
+  const float* scale_a;    // fp8: device scalars, the de-quantisation factors of A and B (epilogue multiplies the accumulator)
+  const float* scale_b;
 };
 
 // Fused collective (tensor-parallel) state.  mode 1: all-gather -> GEMM, mode 2: GEMM -> reduce-scatter.
@@ -640,6 +643,14 @@ EPL_DEVICE void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same tile, e4m3 / e5m2 operands (32 K-elements = 32 bytes per instruction: twice the math per shared-memory byte of bf16)
+EPL_DEVICE void umma_f8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive (when all previously issued MMAs are complete) on the barrier at this smem offset in BOTH CTAs of the pair
 EPL_DEVICE void umma_commit_2cta(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -673,8 +684,10 @@ EPL_DEVICE void red_add_v4_f32(float* p, float a, float b, float c, float d) {
 template <bool kFast>
 EPL_DEVICE void epilogue_chunk32(const GemmParams& p, int row, int col0, const uint32_t (&r)[32], const uint4 (&ax)[4]) {
   float v[32];
+  float alpha = p.alpha;
+  if (p.scale_a != nullptr) alpha *= __ldg(p.scale_a) * __ldg(p.scale_b);     // fp8: per-tensor de-quantisation factors
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
   if (p.bias != nullptr && (p.epilogue == EPI_BIAS || p.epilogue == EPI_BIAS_GELU || p.epilogue == EPI_BIAS_RESIDUAL)) {
     const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
     if (kFast) {
@@ -920,7 +933,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int m_blocks = (p.M + BM2 - 1) / BM2;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int num_tiles = m_blocks * n_blocks;
-  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int block_k = p.fp8 ? 2 * BLOCK_K : BLOCK_K;        // elements per 128-byte k-block
+  const int k_blocks = (p.K + block_k - 1) / block_k;
   const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -972,7 +986,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           unsigned char* sa = smem + stage * kStageBytes;
           unsigned char* sb = sa + kABytes;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);             // bytes of both CTAs land on the leader's barrier
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * block_k;
           if (!p.a_mn_major) {
             tma_load_2d_2cta(sa, &map_a, &full_bar[stage], k0, m0);
           } else {
@@ -1015,7 +1029,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            umma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0);
+            if (p.fp8) umma_f8_2cta(tmem_d, da, db, idesc, (kb | k) != 0);
+            else umma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0);
           }
           umma_commit_2cta(&empty_bar[stage]);
           if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc]);
@@ -1134,7 +1149,7 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
     GemmParams p2;
     p2.M = M; p2.N = N; p2.K = K; p2.ldd = ldd; p2.D = D; p2.bias = bias; p2.pre = pre; p2.aux = aux; p2.epilogue = epilogue;
     p2.accumulate = accumulate; p2.out_dtype = out_dtype; p2.a_mn_major = a_mn_major; p2.b_mn_major = b_mn_major; p2.alpha = alpha;
-    p2.ab_format = is_fp16 ? 0 : 1; p2.bn2 = bn2;
+    p2.ab_format = is_fp16 ? 0 : 1; p2.bn2 = bn2; p2.fp8 = 0; p2.scale_a = p2.scale_b = nullptr;
     return launch_gemm2(ma2, mb2, p2, sms, (cudaStream_t)stream);
   }
   const int bn = pick_bn(N, b_mn_major, two_cta_forced ? 0 : force_bn);
@@ -1149,12 +1164,47 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.D = D; p.bias = bias; p.pre = pre; p.aux = aux; p.epilogue = epilogue;
   p.accumulate = accumulate; p.out_dtype = out_dtype; p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.alpha = alpha; p.ab_format = is_fp16 ? 0 : 1;
+  p.fp8 = 0; p.scale_a = p.scale_b = nullptr; p.sched_counter = nullptr; p.bn2 = 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (num_sms <= 0) num_sms = kNumSMs;
   CommParams c{};
   if (bn == 256) return launch_gemm<256, COMM_NONE>(ma, mb, p, c, num_sms, st);
   if (bn == 160) return launch_gemm<160, COMM_NONE>(ma, mb, p, c, num_sms, st);
   return launch_gemm<128, COMM_NONE>(ma, mb, p, c, num_sms, st);
+}
+
+// 1-byte tensor map: [rows, cols] of e4m3, cols contiguous, row stride ld bytes, box {128 bytes, box_rows}, 128B swizzle
+static int make_map_2d_u8(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -10;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
+// fp8 (e4m3 x e4m3 -> fp32 accumulate) forward GEMM on the 2-CTA kernel: D[M,N] = (A_q[M,K] @ B_q[N,K]^T) * scale_a * scale_b
+// (+ the usual epilogues).  A_q / B_q come from epl_quantize_e4m3 (csrc/act.cu) together with their de-quantisation factors.
+extern "C" int epl_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                            const void* bias, void* pre, const void* aux, int epilogue, int out_dtype, float alpha,
+                            const void* scale_a, const void* scale_b, int num_sms, void* stream) {
+  if (M < 256 || N < 256 || (K & 15) || (lda & 15) || (ldb & 15)) return -21;
+  const int sms = num_sms > 0 ? num_sms : kNumSMs;
+  const int bn2 = pick_bn2(M, N, sms);
+  CUtensorMap ma, mb;
+  int rc = make_map_2d_u8(&ma, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map_2d_u8(&mb, B, N, K, ldb, bn2 / 2);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.D = D; p.bias = bias; p.pre = pre; p.aux = aux; p.epilogue = epilogue;
+  p.accumulate = 0; p.out_dtype = out_dtype; p.a_mn_major = 0; p.b_mn_major = 0; p.alpha = alpha;
+  p.ab_format = 0;                               // kind::f8f6f4 format code 0 = E4M3
+  p.bn2 = bn2; p.fp8 = 1; p.scale_a = (const float*)scale_a; p.scale_b = (const float*)scale_b;
+  return launch_gemm2(ma, mb, p, sms, (cudaStream_t)stream);
 }
 
 // Fused tensor-parallel GEMMs.  mode 1 (all-gather -> GEMM): A is the local gathered buffer `ag_dst` [M, K] which the
@@ -1176,6 +1226,7 @@ extern "C" int epl_gemm_fused(int mode, const void* A, const void* B, int M, int
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.D = D; p.bias = bias; p.pre = pre; p.aux = nullptr; p.epilogue = epilogue;
   p.accumulate = 0; p.out_dtype = is_fp16 ? EPL_F16 : EPL_BF16; p.a_mn_major = 0; p.b_mn_major = b_mn_major; p.alpha = 1.f;
   p.ab_format = is_fp16 ? 0 : 1;
+  p.fp8 = 0; p.scale_a = p.scale_b = nullptr; p.sched_counter = nullptr; p.bn2 = 0;
   CommParams c{};
   c.rank = rank; c.world = world; c.epoch = epoch; c.copy_ctas = copy_ctas;
   c.rows_per_rank = (mode == COMM_AGB ? N : M) / world;

@@ -15,6 +15,7 @@ namespace epl {
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, grad_scale, inv_c1, inv_c2;
   int vec_ok;
+  const float* dyn;      // optional device {lr, inv_c1, inv_c2, grad_scale}: overrides the launch values (CUDA-graph replays)
 };
 
 template <typename G, typename O, bool kHasOut, bool kHasMask>
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, 
                                                      float* __restrict__ m, float* __restrict__ v,
                                                      O* __restrict__ out, const float* __restrict__ mask,
                                                      int64_t n, AdamArgs a) {
+  if (a.dyn != nullptr) { a.lr = a.dyn[0]; a.inv_c1 = a.dyn[1]; a.inv_c2 = a.dyn[2]; a.grad_scale = a.dyn[3]; }
   const int64_t nvec = a.vec_ok ? (n >> 2) : 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -150,7 +152,20 @@ extern "C" int epl_adamw(void* master, const void* grad, int grad_dtype, void* m
   auto al = [](const void* p, uintptr_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
   int vec_ok = al(master, 16) && al(m, 16) && al(v, 16) && al(mask, 16) && al(grad, grad_dtype == EPL_F32 ? 16 : 8) &&
                al(out, out_dtype == EPL_F32 ? 16 : 8);
-  AdamArgs a{lr, beta1, beta2, eps, weight_decay, grad_scale, inv_c1, inv_c2, vec_ok};
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay, grad_scale, inv_c1, inv_c2, vec_ok, nullptr};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DISPATCH2(grad_dtype, out_dtype, launch_adamw, (float*)master, grad, (float*)m, (float*)v, out, (const float*)mask,
+            n, a, st);
+}
+
+// same, with the per-step values {lr, inv_c1, inv_c2, grad_scale} read from device memory: the launch is step-invariant
+extern "C" int epl_adamw_dyn(void* master, const void* grad, int grad_dtype, void* m, void* v, void* out, int out_dtype,
+                             const void* mask, int64_t n, const void* dyn, float beta1, float beta2, float eps,
+                             float weight_decay, void* stream) {
+  auto al = [](const void* p, uintptr_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+  int vec_ok = al(master, 16) && al(m, 16) && al(v, 16) && al(mask, 16) && al(grad, grad_dtype == EPL_F32 ? 16 : 8) &&
+               al(out, out_dtype == EPL_F32 ? 16 : 8);
+  AdamArgs a{0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, 1.f, vec_ok, (const float*)dyn};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DISPATCH2(grad_dtype, out_dtype, launch_adamw, (float*)master, grad, (float*)m, (float*)v, out, (const float*)mask,
             n, a, st);

@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(512, 1) fused_rs_adam_ag_kernel(const FusedDpA
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kK1Piece = 2048;                    // elements per piece (4 KB of bf16 per peer)
 constexpr int kK1Threads = kK1Piece / 8;          // one 16-byte vector per thread per piece
-constexpr int kK1OutBufs = 3;
+constexpr int kK1OutBufs = 8;                     // weight staging buffers: kK1OutBufs - 1 store groups in flight per CTA (a peer
+                                                  // store keeps its source buffer for an NVLink round trip: with 3 buffers
+                                                  // a CTA moved one 4 KB piece per ~2 us regardless of everything else)
 
 struct FusedDpDyn {                               // device-resident, updated by a tiny kernel / memcpy before each step
   float lr, inv_c1, inv_c2, grad_scale;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) fused_rs_adam_ag_v2_kernel(cons
         bulk_s2g(reinterpret_cast<G*>(a.params.ptr[dst]) + a.shard_start + e0, ob, bytes);
       }
       tma_store_commit();
-      tma_store_wait_read<1>();                                             // the staging buffer of the previous piece is free again
+      tma_store_wait_read<kK1OutBufs - 2>();                                // the staging buffer the NEXT piece will use is free again
     }
   }
   if (tid == 0) {
@@ -526,13 +528,17 @@ __global__ void __launch_bounds__(512) alltoall_p2p_kernel(const A2AArgs a) {
   __shared__ int is_last;
   if (threadIdx.x == 0) {
     __threadfence_system();
-    is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x * a.epoch - 1);
+    is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x - 1);          // the last CTA resets the counter (grid may vary per call)
   }
   __syncthreads();
-  if (is_last && threadIdx.x < a.world) {
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + kMaxPeers + a.rank, a.epoch);
-    while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + kMaxPeers + threadIdx.x) < a.epoch) {}
+  if (is_last) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + kMaxPeers + a.rank, a.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + kMaxPeers + threadIdx.x) < a.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { a.local_sync[1] = 0u; __threadfence(); }
   }
 }
 }  // namespace epl
@@ -549,5 +555,87 @@ extern "C" int epl_alltoall_p2p(const void* send, void* const* recv_ptrs, void* 
   a.rank = rank; a.world = world; a.epoch = epoch;
   if (blocks <= 0) blocks = 64;
   epl::alltoall_p2p_kernel<<<std::min(blocks, epl::kNumSMs), 512, 0, (cudaStream_t)stream>>>(a);
+  return EPL_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5b — MoE dispatch fused into the all-to-all: the routed [E, C, M] tensor is never materialised.  `index[e*C + c]` is the
+// row of `x` ([tokens, M] bf16/fp16) routed to slot c of expert e, or -1 for an empty slot.  Each slot is read from `x`
+// (or zero-filled) and stored straight into the destination rank's symmetric receive buffer, laid out
+// [local expert][src rank][C][M] — what the expert GEMMs consume (T = world * C rows per local expert).  One warp per slot, 16-byte vectors.
+// (Reference: einsum "gsec,gsm->egcm" followed by 2*world ncclSend/Recv, parallel/hooks.py:758-794.)
+// ---------------------------------------------------------------------------------------------------------
+namespace epl {
+struct A2AGatherArgs {
+  PeerTable recv;           // every rank's receive buffer [e_local][world][C][M]
+  PeerTable flags;
+  const int4* x;            // local tokens [tokens, M]
+  const int* index;         // [E * C]
+  uint32_t* local_sync;
+  int64_t row_vecs;         // 16-byte vectors per row (M * 2 / 16)
+  int E, C, e_local;
+  int rank, world;
+  uint32_t epoch;
+};
+
+__global__ void __launch_bounds__(512) alltoall_gather_p2p_kernel(const A2AGatherArgs a) {
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + a.rank, a.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + threadIdx.x) < a.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.local_sync), "r"(a.epoch) : "memory"); }
+  } else if (threadIdx.x == 0) {
+    uint32_t v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.local_sync) : "memory"); } while (v < a.epoch);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int64_t slots = (int64_t)a.E * a.C;
+  for (int64_t s0 = (int64_t)blockIdx.x * warps + warp; s0 < slots; s0 += (int64_t)gridDim.x * warps) {
+    // rotate the expert order by rank so that all ranks do not hammer the same destination at the same time
+    const int e = (int)((s0 / a.C + (int64_t)a.rank * a.e_local) % a.E), c = (int)(s0 % a.C);
+    const int row = a.index[(int64_t)e * a.C + c];
+    const int dst = e / a.e_local, el = e - dst * a.e_local;
+    int4* out = reinterpret_cast<int4*>(a.recv.ptr[dst]) + (((int64_t)el * a.world + a.rank) * a.C + c) * a.row_vecs;   // [e_local][src][C][M]
+    const int4* in = a.x + (int64_t)max(row, 0) * a.row_vecs;
+    for (int64_t v = lane; v < a.row_vecs; v += 32) {
+      int4 val = row >= 0 ? in[v] : make_int4(0, 0, 0, 0);
+      st_peer(out + v, val);
+    }
+  }
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + kMaxPeers + a.rank, a.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + kMaxPeers + threadIdx.x) < a.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { a.local_sync[1] = 0u; __threadfence(); }
+  }
+}
+}  // namespace epl
+
+extern "C" int epl_alltoall_gather_p2p(const void* x, const void* index, void* const* recv_ptrs, void* const* flag_ptrs, void* local_sync,
+                                       int64_t row_bytes, int E, int C, int rank, int world, unsigned epoch, int blocks, void* stream) {
+  if (world > epl::kMaxPeers || (row_bytes & 15) || E % world) return -20;
+  epl::A2AGatherArgs a;
+  for (int i = 0; i < epl::kMaxPeers; ++i) {
+    a.recv.ptr[i] = i < world ? recv_ptrs[i] : nullptr;
+    a.flags.ptr[i] = i < world ? flag_ptrs[i] : nullptr;
+  }
+  a.x = (const int4*)x; a.index = (const int*)index; a.local_sync = (uint32_t*)local_sync; a.row_vecs = row_bytes / 16;
+  a.E = E; a.C = C; a.e_local = E / world; a.rank = rank; a.world = world; a.epoch = epoch;
+  if (blocks <= 0) blocks = 64;
+  epl::alltoall_gather_p2p_kernel<<<std::min(blocks, epl::kNumSMs), 512, 0, (cudaStream_t)stream>>>(a);
   return EPL_CHECK_LAUNCH();
 }

@@ -55,6 +55,7 @@ _p, _i, _l, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
 class _Sigs:
   epl_adamw = [_p, _p, _i, _p, _p, _p, _i, _p, _l, _f, _f, _f, _f, _f, _f, _f, _f, _p]
+  epl_adamw_dyn = [_p, _p, _i, _p, _p, _p, _i, _p, _l, _p, _f, _f, _f, _f, _p]
   epl_sgd = [_p, _p, _i, _p, _p, _i, _l, _f, _f, _f, _f, _p]
   epl_sumsq = [_p, _i, _l, _p, _p]
   epl_norm_fwd = [_p, _p, _p, _p, _p, _p, _i, _i, _f, _i, _i, _p]
@@ -66,6 +67,8 @@ class _Sigs:
   epl_add = [_p, _p, _p, _l, _i, _p]
   epl_xent = [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _l, _i, _i, _i, _p]
   epl_scale_by_device_scalar = [_p, _p, _l, _i, _p]
+  epl_gemm_fp8 = [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _f, _p, _p, _i, _p]
+  epl_quantize_e4m3 = [_p, _i, _l, _p, _p, _p, _p]
   epl_gemm = [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _f, _i, _i, _i, _p]
 
 

@@ -10,10 +10,19 @@ from easyparallellibrary_b200.ops import _lib
 
 def adamw_step(master: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, hyper,
                grad_scale: float = 1.0, decay_mask: Optional[torch.Tensor] = None,
-               model_out: Optional[torch.Tensor] = None) -> None:
+               model_out: Optional[torch.Tensor] = None, dyn: Optional[torch.Tensor] = None) -> None:
+  """``dyn``: device tensor {lr, 1/(1-b1^t), 1/(1-b2^t), grad scale}; when given the launch carries no per-step value
+  (CUDA-graph replays read the current ones from memory)."""
   lib = _lib.require()
   assert master.dtype == torch.float32 and m.dtype == torch.float32 and v.dtype == torch.float32
   assert master.is_contiguous() and grad.is_contiguous() and grad.numel() == master.numel()
+  if dyn is not None:
+    out_dt = _lib.dtype_code(model_out.dtype) if model_out is not None else _lib.F32
+    rc = lib.epl_adamw_dyn(master.data_ptr(), grad.data_ptr(), _lib.dtype_code(grad.dtype), m.data_ptr(), v.data_ptr(),
+                           _lib.ptr(model_out), out_dt, _lib.ptr(decay_mask), master.numel(), dyn.data_ptr(), hyper.beta1,
+                           hyper.beta2, hyper.eps, hyper.weight_decay, _lib.stream())
+    _lib.check(rc, "adamw")
+    return
   if hyper.bias_correction:
     inv_c1 = 1.0 / (1.0 - hyper.beta1 ** step)
     inv_c2 = 1.0 / (1.0 - hyper.beta2 ** step)

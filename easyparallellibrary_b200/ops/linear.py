@@ -98,12 +98,21 @@ def _sink_weight_grad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> Opti
   return gemm(a, b, a_mn_major=True, b_mn_major=True)
 
 
+def _fwd_gemm(x2: torch.Tensor, w: torch.Tensor):
+  """Forward GEMM of a linear layer: the fp8 path (``amp.level = "fp8"``, ops/fp8.py) when enabled and the shape fits it."""
+  from easyparallellibrary_b200.ops import fp8
+  if fp8.ENABLED and x2.dtype == torch.bfloat16 and w.is_contiguous() and fp8.supported(x2.shape[0], w.shape[0], x2.shape[1]):
+    return fp8.gemm_fp8
+  return gemm
+
+
 class _LinearFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, x, w, bias, gelu, residual=None):
     x2 = x.reshape(-1, x.shape[-1])
     if not x2.is_contiguous():
       x2 = x2.contiguous()
+    gemm = _fwd_gemm(x2, w)
     pre = None
     ctx.has_res = residual is not None
     if residual is not None:
@@ -147,15 +156,16 @@ class _MlpFn(torch.autograd.Function):
     if not x2.is_contiguous():
       x2 = x2.contiguous()
     pre = torch.empty((x2.shape[0], w1.shape[0]), dtype=x.dtype, device=x.device)
-    h = gemm(x2, w1, bias=b1, epilogue=EPI_BIAS_GELU, pre=pre)
+    h = _fwd_gemm(x2, w1)(x2, w1, bias=b1, epilogue=EPI_BIAS_GELU, pre=pre)
+    gemm2_ = _fwd_gemm(h, w2)
     ctx.has_res = residual is not None
     if residual is not None:
       r2 = residual.reshape(-1, w2.shape[0])
       if not r2.is_contiguous():
         r2 = r2.contiguous()
-      y = gemm(h, w2, bias=b2, epilogue=EPI_BIAS_RESIDUAL, aux=r2)
+      y = gemm2_(h, w2, bias=b2, epilogue=EPI_BIAS_RESIDUAL, aux=r2)
     else:
-      y = gemm(h, w2, bias=b2, epilogue=EPI_BIAS if b2 is not None else EPI_NONE)
+      y = gemm2_(h, w2, bias=b2, epilogue=EPI_BIAS if b2 is not None else EPI_NONE)
     ctx.save_for_backward(x2, w1, w2, pre, h)
     ctx.has_b1, ctx.has_b2, ctx.xshape = b1 is not None, b2 is not None, x.shape
     return y.view(*x.shape[:-1], w2.shape[0])

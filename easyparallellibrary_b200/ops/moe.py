@@ -5,10 +5,18 @@ and auxiliary load-balancing loss, ``MoEFFN`` (370-464) whose expert weights are
 (dim 0 = experts, ``hooks.py:667-707``) and whose three einsums trigger an all-to-all *dispatch* before the first
 and an all-to-all *combine* before the third (``hooks.py:758-794``).
 
-Here the layer is explicit: gating -> dispatch einsum -> all-to-all -> expert FFN (batched GEMMs over the local
-experts) -> all-to-all -> combine einsum.  On B200 the all-to-all is one hand-written kernel that stores each
-segment straight into the destination rank's symmetric receive buffer over NVLink
-(``csrc/symm.cu: alltoall_p2p_kernel``); NCCL send/recv is the CPU/baseline path.  The all-to-all is never
+Here the layer is explicit and index based: gating produces, per token, the (expert, slot) of each of its choices — the
+reference's dense one-hot dispatch/combine tensors ``[G,S,E,C]`` and their ``O(S*E*C*M)`` einsums are never built; dispatch
+is a row gather, combine a weighted row gather (``O(S*k*M)``).  On B200:
+
+* **dispatch + all-to-all are one kernel** (``csrc/symm.cu: alltoall_gather_p2p_kernel``, K5b): every (expert, slot) row is
+  read from the local token matrix and stored straight into the owning rank's symmetric receive buffer over NVLink, already
+  in the ``[local expert, source rank x slots, M]`` layout the expert GEMMs consume;
+* **expert FFNs run on the tcgen05 GEMM** (one launch per local expert and projection, all three of forward / dX / dW
+  without transposes);
+* the combine all-to-all is the peer-store kernel ``alltoall_p2p_kernel`` (K5).
+
+NCCL all-to-all + einsum experts is the CPU / baseline path (``USE_P2P_KERNEL = False``).  The all-to-all is never
 recomputed by gradient checkpointing (``epl_collective``), like the reference (``constant.py:97``).
 """
 from __future__ import annotations
@@ -21,10 +29,10 @@ from torch import nn
 
 from easyparallellibrary_b200.communicators import functional as CF
 
-# The peer-store all-to-all kernel has not been exercised on hardware yet (tools/mgpu_check.py moe is the check); until it
-# has, NCCL grouped send/recv is the default transport and EPL_MOE_P2P=1 opts in.
+# peer-store all-to-all kernels (K5 / K5b) on GPUs; EPL_MOE_P2P=0 selects NCCL (the baseline arm of tools/mgpu_check.py moe)
 import os as _os
-USE_P2P_KERNEL = _os.environ.get("EPL_MOE_P2P", "0") == "1"
+USE_P2P_KERNEL = _os.environ.get("EPL_MOE_P2P", "1") == "1"
+USE_EXPERT_GEMM = _os.environ.get("EPL_MOE_GEMM", "1") == "1"
 _A2A_WS: Dict[int, "_A2AWorkspace"] = {}
 
 
@@ -95,14 +103,117 @@ def expert_all_to_all(t: torch.Tensor, group) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------------
+# fused dispatch + all-to-all (K5b)
+# --------------------------------------------------------------------------------------------------------
+def _p2p_dispatch(x2: torch.Tensor, index: torch.Tensor, E: int, slots: int, group) -> torch.Tensor:
+  """``x2`` [tokens, M], ``index`` [E * slots] int32 (row of x2 or -1) -> [E_local, world * slots, M] on every rank."""
+  from easyparallellibrary_b200.ops import _lib
+  from easyparallellibrary_b200.runtime.symmetric import _sym_lib
+  lib = _sym_lib()
+  if not hasattr(lib, "_a2ag_ready"):
+    lib.epl_alltoall_gather_p2p.argtypes = ([ctypes.c_void_p] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 4 + [ctypes.c_uint, ctypes.c_int,
+                                                                                                    ctypes.c_void_p])
+    lib._a2ag_ready = True
+  ws = _A2A_WS.get(id(group))
+  if ws is None:
+    ws = _A2A_WS[id(group)] = _A2AWorkspace(group, x2.device)
+  M = x2.shape[1]
+  e_local = E // group.size
+  nbytes = group.size * e_local * slots * M * x2.element_size()
+  buf = ws.recv_buffer(nbytes)
+  ws.epoch += 1
+  rc = lib.epl_alltoall_gather_p2p(x2.data_ptr(), index.data_ptr(), buf.peer_table(0), ws.pad.slot_table(0), ws.sync.data_ptr(),
+                                   M * x2.element_size(), E, slots, group.rank, group.size, ws.epoch, 96, _lib.stream())
+  _lib.check(rc, "alltoall_gather_p2p")
+  return buf.tensor(x2.dtype, group.size * e_local * slots * M).view(e_local, group.size * slots, M).clone()
+
+
+class _Dispatch(torch.autograd.Function):
+  """tokens [T, M] + slot table -> expert inputs [E_local, world * slots, M] (gather + all-to-all); the adjoint is the
+  all-to-all back + a scatter-add of the slot gradients onto their tokens."""
+
+  @staticmethod
+  def forward(ctx, x2, index, E, slots, group):
+    ctx.group, ctx.E, ctx.slots, ctx.T = group, E, slots, x2.shape[0]
+    ctx.save_for_backward(index)
+    n, e_local, M = group.size, E // group.size, x2.shape[1]
+    if (USE_P2P_KERNEL and x2.is_cuda and n > 1 and n <= 8 and (M * x2.element_size()) % 16 == 0 and x2.is_contiguous()
+        and x2.dtype in (torch.bfloat16, torch.float16)):
+      return _p2p_dispatch(x2, index, E, slots, group)
+    pad = torch.cat([x2, x2.new_zeros(1, M)], 0)
+    routed = pad[index.long()]                                           # [E * slots, M]; index -1 -> the zero row
+    if n > 1:
+      routed = expert_all_to_all_raw(routed.view(n, e_local * slots * M), group).view(n, e_local, slots, M)
+      routed = routed.permute(1, 0, 2, 3).reshape(e_local, n * slots, M)
+    else:
+      routed = routed.view(E, slots, M)
+    return routed
+
+  @staticmethod
+  def backward(ctx, g):
+    (index,) = ctx.saved_tensors
+    group, E, slots = ctx.group, ctx.E, ctx.slots
+    n, e_local, M = group.size, E // group.size, g.shape[-1]
+    g = g.contiguous()
+    if n > 1:
+      g = g.view(e_local, n, slots, M).permute(1, 0, 2, 3).contiguous()
+      g = expert_all_to_all_raw(g.view(n, -1), group)
+    g = g.reshape(E * slots, M)
+    dx = g.new_zeros(ctx.T + 1, M)
+    dx.index_add_(0, torch.where(index < 0, torch.full_like(index, ctx.T), index).long(), g)
+    return dx[:ctx.T], None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------------
+# expert GEMMs on the tcgen05 kernel
+# --------------------------------------------------------------------------------------------------------
+class _ExpertGemm(torch.autograd.Function):
+  """``y[e] = x[e] @ w[e]`` for the local experts: x [E, T, K], w [E, K, N].  One tcgen05 GEMM launch per expert; forward
+  (B MN-major), dX (B K-major) and dW (both operands MN-major) all read the tensors as they are."""
+
+  @staticmethod
+  def forward(ctx, x, w):
+    from easyparallellibrary_b200.ops.linear import gemm
+    ctx.save_for_backward(x, w)
+    y = x.new_empty(x.shape[0], x.shape[1], w.shape[2])
+    for e in range(x.shape[0]):
+      gemm(x[e], w[e], b_mn_major=True, out=y[e])
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    from easyparallellibrary_b200.ops.linear import gemm
+    x, w = ctx.saved_tensors
+    dy = dy.contiguous()
+    dx, dw = torch.empty_like(x), torch.empty_like(w)
+    for e in range(x.shape[0]):
+      gemm(dy[e], w[e], out=dx[e])                                       # [T, N] x ([K, N] read as N_out=K, contraction N)
+      gemm(x[e], dy[e], a_mn_major=True, b_mn_major=True, out=dw[e])     # x^T dy -> [K, N]
+    return dx, dw
+
+
+def expert_matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+  """[E, T, K] x [E, K, N] -> [E, T, N]."""
+  from easyparallellibrary_b200.ops import _lib
+  ok = (USE_EXPERT_GEMM and x.is_cuda and _lib.available() and x.dtype in (torch.bfloat16, torch.float16) and w.dtype == x.dtype
+        and x.shape[2] % 8 == 0 and w.shape[2] % 8 == 0 and x.is_contiguous() and w.is_contiguous() and x.shape[1] >= 8)
+  if ok:
+    return _ExpertGemm.apply(x, w)
+  return torch.einsum("etk,ekn->etn", x, w.to(x.dtype))
+
+
+# --------------------------------------------------------------------------------------------------------
 # gating
 # --------------------------------------------------------------------------------------------------------
 def _capacity(tokens: int, experts: int, factor: float, minimum: int = 4) -> int:
   return max(int(tokens * factor / experts), minimum)
 
 
-class SwitchGating(nn.Module):
-  """Top-1 routing.  Returns (dispatch [G,S,E,C] bool-ish, combine [G,S,E,C], aux_loss)."""
+class _Gating(nn.Module):
+  """Shared routing logic.  ``route(x)`` -> ``(slots [G,S,k] int64 in [0, E*C) or -1, weights [G,S,k], C, aux)``: choice j of
+  token s goes to expert ``slot // C`` at position ``slot % C`` (capacity overflow: -1, weight 0).  ``forward`` builds the
+  reference's dense ``(dispatch, combine, aux)`` triple from it (API parity with examples/moe/moe_ffn.py; not used by MoEFFN)."""
+  k = 1
 
   def __init__(self, d_model: int, num_experts: int, capacity_factor: float = 1.25):
     super().__init__()
@@ -110,53 +221,62 @@ class SwitchGating(nn.Module):
     nn.init.normal_(self.w, std=d_model ** -0.5)
     self.E, self.cf = num_experts, capacity_factor
 
-  def forward(self, x):                                   # [G, S, M]
+  def route(self, x):
+    raise NotImplementedError
+
+  def forward(self, x):
+    slots, weights, C, aux = self.route(x)
+    G, S, _ = x.shape
+    combine = x.new_zeros(G, S, self.E * C, dtype=torch.float32)
+    for j in range(slots.shape[-1]):
+      sj, wj = slots[..., j], weights[..., j]
+      combine.scatter_add_(2, sj.clamp(min=0).unsqueeze(-1), (wj * (sj >= 0)).unsqueeze(-1).float())
+    combine = combine.view(G, S, self.E, C)
+    return (combine > 0).to(x.dtype), combine.to(x.dtype), aux
+
+
+class SwitchGating(_Gating):
+  """Top-1 routing with capacity and the load-balancing auxiliary loss."""
+  k = 1
+
+  def route(self, x):                                     # [G, S, M]
     G, S, _ = x.shape
     C = _capacity(S, self.E, self.cf)
     gates = torch.softmax((x.float() @ self.w.float()), -1)          # [G,S,E]
     idx = gates.argmax(-1)
     mask = torch.nn.functional.one_hot(idx, self.E).float()
-    density, density_proxy = mask.mean(1), gates.mean(1)
-    aux = (density * density_proxy).mean() * self.E * self.E
-    pos = torch.cumsum(mask, 1) * mask - mask                         # position of each token inside its expert
-    mask = mask * (pos < C)
-    gate = (gates * mask).sum(-1, keepdim=True)
-    pos_oh = torch.nn.functional.one_hot(pos.sum(-1).long().clamp(max=C - 1), C).float()
-    combine = gate.unsqueeze(-1) * mask.unsqueeze(-1) * pos_oh.unsqueeze(2)   # [G,S,E,C]
-    return (combine > 0).to(x.dtype), combine.to(x.dtype), aux
+    aux = (mask.mean(1) * gates.mean(1)).mean() * self.E * self.E
+    pos = ((torch.cumsum(mask, 1) - 1) * mask).sum(-1).long()         # position of each token inside its expert
+    keep = pos < C
+    gate = gates.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
+    slots = torch.where(keep, idx * C + pos, torch.full_like(idx, -1)).unsqueeze(-1)
+    return slots, (gate * keep).unsqueeze(-1), C, aux
 
 
-class Top2Gating(nn.Module):
-  """Top-2 routing with capacity (second choice taken after first choices are placed)."""
+class Top2Gating(_Gating):
+  """Top-2 routing with capacity (second choices are placed after all first choices)."""
+  k = 2
 
-  def __init__(self, d_model: int, num_experts: int, capacity_factor: float = 1.25):
-    super().__init__()
-    self.w = nn.Parameter(torch.empty(d_model, num_experts))
-    nn.init.normal_(self.w, std=d_model ** -0.5)
-    self.E, self.cf = num_experts, capacity_factor
-
-  def forward(self, x):
+  def route(self, x):
     G, S, _ = x.shape
     C = _capacity(2 * S, self.E, self.cf)
     gates = torch.softmax((x.float() @ self.w.float()), -1)
     i1 = gates.argmax(-1)
     m1 = torch.nn.functional.one_hot(i1, self.E).float()
-    g2 = gates * (1 - m1)
-    i2 = g2.argmax(-1)
+    i2 = (gates * (1 - m1)).argmax(-1)
     m2 = torch.nn.functional.one_hot(i2, self.E).float()
     aux = (m1.mean(1) * gates.mean(1)).mean() * self.E * self.E
-    p1 = torch.cumsum(m1, 1) * m1 - m1
-    m1 = m1 * (p1 < C)
-    used = m1.sum(1, keepdim=True)
-    p2 = (torch.cumsum(m2, 1) - m2 + used) * m2
-    m2 = m2 * (p2 < C)
-    w1, w2 = (gates * m1).sum(-1), (gates * m2).sum(-1)
+    p1 = ((torch.cumsum(m1, 1) - 1) * m1).sum(-1).long()
+    k1 = p1 < C
+    used = (m1 * k1.unsqueeze(-1)).sum(1, keepdim=True)               # first choices actually placed per expert
+    p2 = ((torch.cumsum(m2, 1) - 1 + used) * m2).sum(-1).long()
+    k2 = p2 < C
+    w1 = gates.gather(-1, i1.unsqueeze(-1)).squeeze(-1) * k1
+    w2 = gates.gather(-1, i2.unsqueeze(-1)).squeeze(-1) * k2
     denom = (w1 + w2).clamp(min=1e-9)
-    w1, w2 = w1 / denom, w2 / denom
-    oh = lambda p: torch.nn.functional.one_hot(p.sum(-1).long().clamp(max=C - 1), C).float()
-    combine = (w1[..., None, None] * m1.unsqueeze(-1) * oh(p1 * m1).unsqueeze(2) +
-               w2[..., None, None] * m2.unsqueeze(-1) * oh(p2 * m2).unsqueeze(2))
-    return (combine > 0).to(x.dtype), combine.to(x.dtype), aux
+    s1 = torch.where(k1, i1 * C + p1, torch.full_like(i1, -1))
+    s2 = torch.where(k2, i2 * C + p2, torch.full_like(i2, -1))
+    return torch.stack([s1, s2], -1), torch.stack([w1 / denom, w2 / denom], -1), C, aux
 
 
 class MoEFFN(nn.Module):
@@ -179,17 +299,29 @@ class MoEFFN(nn.Module):
 
   def forward(self, x):                                   # [G, S, M]
     G, S, M = x.shape
-    dispatch, combine, aux = self.gate(x)
+    slots, weights, C, aux = self.gate.route(x)            # [G,S,k]
     self.aux_loss = aux
-    C = dispatch.shape[-1]
-    routed = torch.einsum("gsec,gsm->egcm", dispatch, x)                 # einsum 1: dispatch
-    n = self.group.size
+    n, E = self.group.size, self.E
+    k = slots.shape[-1]
+    # slot table: index[e, g, c] = row of the flattened token matrix routed there (or -1); slot = e*C + c inside group g
+    g_ids = torch.arange(G, device=x.device).view(G, 1, 1).expand(G, S, k)
+    rows = (g_ids * S + torch.arange(S, device=x.device).view(1, S, 1)).reshape(-1)
+    flat = slots.reshape(-1)
+    e_idx, c_idx = torch.div(flat.clamp(min=0), C, rounding_mode="floor"), flat.clamp(min=0) % C
+    dest = (e_idx * G + g_ids.reshape(-1)) * C + c_idx                 # position in [E, G, C]
+    index = torch.full((E * G * C + 1,), -1, dtype=torch.int32, device=x.device)
+    index.scatter_(0, torch.where(flat >= 0, dest, torch.full_like(dest, E * G * C)), rows.to(torch.int32))
+    index = index[:E * G * C].contiguous()
+    x2 = x.reshape(G * S, M)
+    routed = _Dispatch.apply(x2 if x2.is_contiguous() else x2.contiguous(), index, E, G * C, self.group)    # [E_local, n*G*C, M]
+    h = torch.relu(expert_matmul(routed, self.wi.to(x.dtype)))
+    out = expert_matmul(h, self.wo.to(x.dtype))                        # [E_local, n*G*C, M]
     if n > 1:
-      routed = expert_all_to_all(routed.reshape(n, self.E_local, G, C, M), self.group)       # [src, E_local, G, C, M]
-      routed = routed.permute(1, 0, 2, 3, 4).reshape(self.E_local, n * G, C, M)
-    h = torch.relu(torch.einsum("egcm,emh->egch", routed, self.wi.to(x.dtype)))                # einsum 2
-    out = torch.einsum("egch,ehm->egcm", h, self.wo.to(x.dtype))                               # einsum 3 (expert side)
-    if n > 1:
-      out = out.reshape(self.E_local, n, G, C, M).permute(1, 0, 2, 3, 4).contiguous()
-      out = expert_all_to_all(out, self.group).reshape(self.E, G, C, M)
-    return torch.einsum("gsec,egcm->gsm", combine, out)                  # combine
+      out = out.view(self.E_local, n, G * C * M)
+      out = out.permute(1, 0, 2).contiguous() if self.E_local > 1 else out.view(n, G * C * M)
+      out = expert_all_to_all(out, self.group)                         # [src rank, E_local * G*C*M] = experts in global order
+    out = out.reshape(E * G * C, M)
+    # combine: y[token] = sum_j weight_j * out[slot_j]
+    pad = torch.cat([out, out.new_zeros(1, M)], 0)
+    gathered = pad[torch.where(flat >= 0, dest, torch.full_like(dest, E * G * C))].view(G, S, k, M)
+    return (gathered * weights.to(x.dtype).unsqueeze(-1)).sum(2)

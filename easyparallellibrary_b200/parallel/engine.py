@@ -96,7 +96,7 @@ class Trainer(object):
   def __init__(self, model: nn.Module, optimizer: str = "adamw", loss_fn: Optional[Callable] = None,
                device: Optional[torch.device] = None, max_grad_norm: Optional[float] = None,
                no_decay: Callable[[nn.Parameter], bool] = default_no_decay, example_inputs: Optional[Sequence[Any]] = None,
-               baseline: bool = False, **opt_kwargs):
+               baseline: bool = False, cuda_graph: Optional[bool] = None, **opt_kwargs):
     env = Env.get()
     if not env.is_initialized:
       env.init(None)
@@ -116,6 +116,7 @@ class Trainer(object):
     self.no_decay = no_decay
     self.example_inputs = example_inputs
     self.baseline = baseline            # reference-equivalent library path (all-reduce + unfused optimizer)
+    self.cuda_graph = cuda_graph        # True: capture the whole step in a CUDA graph when the configuration allows it
     self._device = device
     self._built = False
     self.global_step = 0
@@ -155,6 +156,8 @@ class Trainer(object):
     # ---- precision, placement, recompute ---------------------------------------------
     self.compute_dtype = amp_lib.compute_dtype(cfg.amp.level)
     self.o1 = (cfg.amp.level or "").lower() == "o1"       # fp32 parameters, per-op fp16/fp32 policy (runtime/amp.py)
+    from easyparallellibrary_b200.ops import fp8 as fp8_lib
+    fp8_lib.ENABLED = (cfg.amp.level or "").lower() == "fp8" and self.device.type == "cuda"
     env.parallel_plan = self.plan
     for m in local:
       if self.compute_dtype is not None:
@@ -303,6 +306,16 @@ class Trainer(object):
     if self.plan.pipeline:
       from easyparallellibrary_b200.parallel.pipeline import PipelineExecutor
       self.pipe = PipelineExecutor(self)
+    self._graphed = None
+    self._capturing = False
+    import os as _os
+    want = self.cuda_graph if self.cuda_graph is not None else (_os.environ.get("EPL_CUDA_GRAPH", "0") == "1")
+    if want and self.device.type == "cuda":
+      from easyparallellibrary_b200.parallel.graph_step import GraphedStep
+      if GraphedStep.eligible(self):
+        self._graphed = GraphedStep(self)
+      else:
+        get_logger().info("cuda_graph requested but this configuration is not capturable; running eagerly")
     self._built = True
     return self
 
@@ -459,9 +472,42 @@ class Trainer(object):
     for h in self.hooks:
       h.before_step(self)
     cfg = self.config
-    M = cfg.pipeline.num_micro_batch
     mean = cfg.communication.gradients_reduce_method == constant.REDUCE_MEAN
     self._mean = mean
+    graph = Graph.get()
+    batch = tuple(_to_device(x, self.device) for x in batch)
+    if self.compute_dtype is not None and batch and isinstance(batch[0], torch.Tensor) and batch[0].is_floating_point():
+      batch = (batch[0].to(self.compute_dtype),) + batch[1:]          # the model input follows the compute dtype (AMP)
+    graphed_loss = self._graphed.step(batch, kwargs) if self._graphed is not None else None
+    if graphed_loss is not None:                   # the whole step was one CUDA-graph replay (parallel/graph_step.py)
+      self.global_step += 1
+      out = StepOutput(skipped=False, grad_norm=None, loss_scale=self.scaler.loss_scale, loss=graphed_loss.float().clone())
+    else:
+      if self._graphed is not None:
+        self._graphed._refresh(mean, count=False)
+      losses, collected, skipped, gnorm = self._run_step(batch, kwargs, in_graph=False)
+      self.global_step += 0 if skipped else 1
+      out = StepOutput(skipped=skipped, grad_norm=gnorm, loss_scale=self.scaler.loss_scale)
+      if losses:
+        out.loss = torch.stack([l.float() for l in losses]).mean() if mean else torch.stack([l.float() for l in losses]).sum()
+      out.collections = self._merge_collections(collected)
+    graph.current_micro_batch = None
+    for h in self.hooks:
+      h.after_step(self, out)
+    return out
+
+  def _eager_body(self, batch, kwargs, in_graph: bool = True) -> torch.Tensor:
+    """One full step on ``batch`` (already on the device); used by the CUDA-graph capture.  Returns the loss tensor."""
+    losses, collected, skipped, _ = self._run_step(batch, kwargs, in_graph=in_graph)
+    if any(collected):
+      raise RuntimeError("collections are filled on the host and cannot be replayed from a CUDA graph")
+    return losses[0] if len(losses) == 1 else torch.stack([l.float() for l in losses]).mean()
+
+  def _run_step(self, batch, kwargs, in_graph: bool):
+    """Zero the gradient buckets, forward + backward over the micro-batches (or the pipeline program), reduce + apply."""
+    cfg = self.config
+    M = cfg.pipeline.num_micro_batch
+    mean = self._mean
     graph = Graph.get()
     graph.pop_collections()
     for flat in self.flats.values():
@@ -476,10 +522,11 @@ class Trainer(object):
     for p in self._sink_params:
       p.epl_sink_fresh = True
     if self.fused is not None:
-      self.fused.begin_step(mean)
-    batch = tuple(_to_device(x, self.device) for x in batch)
-    if self.compute_dtype is not None and batch and isinstance(batch[0], torch.Tensor) and batch[0].is_floating_point():
-      batch = (batch[0].to(self.compute_dtype),) + batch[1:]          # the model input follows the compute dtype (AMP)
+      self.fused.reset_step()
+      if in_graph:
+        self.fused._prepared = True                # the host refreshed the device-side step values before the capture / replay
+      else:
+        self.fused.begin_step(mean)
     micro = _split_batch(batch, M)
     losses: List[torch.Tensor] = []
     collected: List["OrderedDict[str, List[Any]]"] = []
@@ -510,15 +557,7 @@ class Trainer(object):
       z.finish_backward()
     with phase_scope(ModelPhase.APPLY):
       skipped, gnorm = self._reduce_and_apply(mean)
-    self.global_step += 0 if skipped else 1
-    out = StepOutput(skipped=skipped, grad_norm=gnorm, loss_scale=self.scaler.loss_scale)
-    if losses:
-      out.loss = torch.stack([l.float() for l in losses]).mean() if mean else torch.stack([l.float() for l in losses]).sum()
-    out.collections = self._merge_collections(collected)
-    graph.current_micro_batch = None
-    for h in self.hooks:
-      h.after_step(self, out)
-    return out
+    return losses, collected, skipped, gnorm
 
   def _check_recompute_gradients(self, mb: Tuple[Any, ...], kwargs) -> None:
     """``gradient_checkpoint.check_gradients`` (reference gc/gradient_checkpoint.py:310-325): before the first step, the

@@ -93,6 +93,14 @@ class FusedDataParallel(object):
       self.dyn[s].copy_(torch.tensor([h.lr, inv_c1, inv_c2, scale], dtype=torch.float32), non_blocking=True)
     self._prepared = True
 
+  def reset_step(self) -> None:
+    """Start of a step: forget per-step launch state (also after a step that was abandoned half-way, e.g. a failed capture)."""
+    self.launched.clear()
+    if self._reserved:
+      from easyparallellibrary_b200.ops import linear as L
+      L._NUM_SMS = 0
+      self._reserved = False
+
   def launch_bucket_async(self, s: int, bi: int) -> None:
     """Called from the gradient hook when the last gradient of a bucket has been produced: the fused kernel runs on
     a side stream while backward continues.  Safe because its first action is a cross-GPU barrier: no rank's weights

@@ -124,6 +124,23 @@ class _NativeP2P(object):
     self._keep.clear()
 
 
+class _StageFn(torch.nn.Module):
+  """What one F instruction runs — the stage's layers and, on the last stage, the loss scaled for backward — as a module
+  of its own, so ``torch.cuda.make_graphed_callables`` can capture it.  Several instances share the same inner module
+  (one per micro-batch that may be in flight: the captured graphs own the saved activations)."""
+
+  def __init__(self, module, loss_fn, factor: float):
+    super().__init__()
+    self.module, self.loss_fn, self.factor = module, loss_fn, float(factor)
+
+  def forward(self, x, *labels):
+    y = self.module(x)
+    if self.loss_fn is not None:
+      y = self.loss_fn(y, *labels)
+      return y * self.factor if self.factor != 1.0 else y
+    return y
+
+
 class PipelineExecutor(object):
   def __init__(self, trainer):
     self.tr = trainer
@@ -161,6 +178,66 @@ class PipelineExecutor(object):
         self.replica_ranks = ranks
     self._shape_fwd: Optional[Tuple[torch.Size, torch.dtype]] = None
     self.device = trainer.device
+    # CUDA graphs of the stage's forward and backward (one pair per micro-batch that can be in flight): a micro-batch of a
+    # few thousand tokens is ~2400 launches of ~30 us kernels, i.e. host-launch bound by 3x when issued from Python
+    # (profiles/r1_bench_pp2_xl_v1.json); replayed from graphs the stage is GPU bound.
+    import os
+    self.use_graphs = (trainer.device.type == "cuda" and os.environ.get("EPL_PIPE_GRAPH", "1") != "0" and not trainer.zero3
+                       and not trainer.config.gradient_checkpoint.type and not trainer.config.offload.level)
+    self.graphed: List[Any] = []
+    self._bufs_f: Dict[int, torch.Tensor] = {}
+    self._bufs_b: Dict[int, torch.Tensor] = {}
+
+  def _in_flight(self) -> int:
+    policy = (self.tr.config.pipeline.strategy or "").lower()
+    if "forward" in policy:                      # GPipe order: every micro-batch is in flight before the first backward
+      return self.M
+    return max(1, min(self.M, self.num_stages - self.stage + (1 if "optimizer" in policy else 0)))
+
+  def _build_graphs(self, micro: List[Tuple[Any, ...]]) -> None:
+    """Capture forward/backward graphs of this stage with ``torch.cuda.make_graphed_callables`` (static input/output buffers,
+    weight gradients of the GEMMs accumulate straight into the flat buckets inside the graph, the remaining parameter
+    gradients come back through autograd).  Any failure leaves the executor on the eager path."""
+    tr = self.tr
+    k = self._in_flight()
+    if k > 4:
+      self.use_graphs = False
+      return
+    mb = micro[0]
+    mean = tr._mean
+    factor = tr.scaler.loss_scale * ((1.0 / self.M) if (mean and self.M > 1) else 1.0)
+    loss_fn = tr.loss_fn if self.last else None
+    if self.last and loss_fn is None:
+      self.use_graphs = False
+      return
+    fns = tuple(_StageFn(self.module, loss_fn, factor if self.last else 1.0) for _ in range(k))
+    if self.first:
+      x = mb[0].clone()
+    else:
+      x = torch.zeros(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
+      if x.is_floating_point():
+        x.requires_grad_()
+    labels = tuple(t.clone() for t in mb[1:] if isinstance(t, torch.Tensor)) if self.last else ()
+    if self.last and len(labels) != len(mb) - 1:
+      self.use_graphs = False
+      return
+    for p in self.module.parameters():           # captured weight-gradient GEMMs must accumulate (the buckets are zeroed per step)
+      if hasattr(p, "epl_sink_fresh"):
+        p.epl_sink_fresh = False
+    tr._first_micro_batch, tr._last_micro_batch = False, False
+    Graph.get().current_micro_batch = mb
+    try:
+      sample = tuple((x.detach().clone().requires_grad_(x.requires_grad),) + labels for _ in range(k))
+      self.graphed = list(torch.cuda.make_graphed_callables(fns, sample, num_warmup_iters=2, allow_unused_input=True))
+    except Exception as e:      # pragma: no cover - depends on the CUDA runtime
+      from easyparallellibrary_b200.utils.logging import get_logger
+      get_logger().warning("pipeline stage %d: CUDA graph capture failed (%s); running the stage eagerly", self.stage, e)
+      self.graphed, self.use_graphs = [], False
+      torch.cuda.synchronize(self.device)
+    Graph.get().pop_collections()
+    for flat in tr.flats.values():               # the warm-up / capture passes ran real weight-gradient GEMMs into the buckets
+      flat.zero_grad()
+    torch.cuda.synchronize(self.device)
 
   # ------------------------------------------------------------------ metadata handshake (first step only)
   def _send_meta(self, t: torch.Tensor) -> None:
@@ -230,6 +307,14 @@ class PipelineExecutor(object):
     if self.device.type == "cuda" and not getattr(self, "_warm", False):
       self._warmup(micro)
       self._warm = True
+      if self.use_graphs:
+        self._build_graphs(micro)
+        dist.barrier(group=self.replica_group)
+    use_graphs = bool(self.graphed) and torch.is_grad_enabled()
+    if use_graphs:
+      for p in self.module.parameters():
+        if hasattr(p, "epl_sink_fresh"):
+          p.epl_sink_fresh = False
     inputs: Dict[int, torch.Tensor] = {}
     outputs: Dict[int, torch.Tensor] = {}
     recv_f: Dict[int, Tuple[torch.Tensor, Any]] = {}
@@ -246,11 +331,18 @@ class PipelineExecutor(object):
       if ins.op == S.RECV_F:
         if self._shape_fwd is None:
           self._shape_fwd = self._recv_meta()
-        buf = torch.empty(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
+        buf = self._bufs_f.get(ins.mb)           # per-micro-batch receive buffers are allocated once and reused every step
+        if buf is None or buf.shape != self._shape_fwd[0]:
+          buf = self._bufs_f[ins.mb] = torch.empty(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
+        else:
+          buf = self._bufs_f[ins.mb] = buf.detach()
+          buf.grad = None
         recv_f[ins.mb] = (buf, self.p2p.recv_fwd(buf))
       elif ins.op == S.RECV_B:
         out = outputs[ins.mb]
-        buf = torch.empty_like(out)
+        buf = self._bufs_b.get(ins.mb)
+        if buf is None or buf.shape != out.shape or buf.dtype != out.dtype:
+          buf = self._bufs_b[ins.mb] = torch.empty_like(out)
         recv_b[ins.mb] = (buf, self.p2p.recv_bwd(buf))
       elif ins.op == S.F:
         mb = micro[ins.mb]
@@ -263,13 +355,19 @@ class PipelineExecutor(object):
           if x.is_floating_point():
             x.requires_grad_()
         with phase_scope(ModelPhase.FORWARD):
-          y = self.module(x)
-          if self.last:
-            loss = tr.loss_fn(y, *mb[1:]) if tr.loss_fn is not None else y
-            losses.append(loss.detach())
-            y = tr.scaler.scale(loss)
-            if mean and self.M > 1:
-              y = y / self.M
+          if use_graphs:
+            fn = self.graphed[ins.mb % len(self.graphed)]
+            y = fn(x, *mb[1:]) if self.last else fn(x)
+            if self.last:
+              losses.append(y.detach() / fn.factor if fn.factor != 1.0 else y.detach().clone())
+          else:
+            y = self.module(x)
+            if self.last:
+              loss = tr.loss_fn(y, *mb[1:]) if tr.loss_fn is not None else y
+              losses.append(loss.detach())
+              y = tr.scaler.scale(loss)
+              if mean and self.M > 1:
+                y = y / self.M
         collected.append(graph.pop_collections())
         inputs[ins.mb], outputs[ins.mb] = x, y
       elif ins.op == S.SEND_F:

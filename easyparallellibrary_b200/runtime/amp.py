@@ -21,7 +21,7 @@ def compute_dtype(level: str) -> Optional[torch.dtype]:
   """Dtype the *parameters* are cast to.  ``bf16``: bf16 weights + fp32 masters in the flat optimizer.  ``O1``: None — the
   parameters stay fp32 (they are the master weights) and precision is decided per op, see :class:`o1_autocast`."""
   level = (level or "").lower()
-  if level == "bf16":
+  if level in ("bf16", "fp8"):                 # fp8: bf16 weights / activations, forward GEMMs quantised per tensor to e4m3 (ops/fp8.py)
     return torch.bfloat16
   return None
 

@@ -97,6 +97,7 @@ class FlatOptimizer(object):
     else:
       raise ValueError("unknown optimizer %r (adam | adamw | sgd)" % kind)
     self.step_count = 0
+    self.dyn: Optional[torch.Tensor] = None        # device {lr, inv_c1, inv_c2, grad scale}: set by the engine in CUDA-graph mode
 
   def step(self, grad_shard: torch.Tensor, model_shard: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
            lo: int = 0, hi: Optional[int] = None, count_step: bool = True) -> None:
@@ -116,7 +117,7 @@ class FlatOptimizer(object):
                              grad_scale, out)
       else:
         fused_optim.adamw_step(self.master[sl], grad_shard[sl], self.m[sl], self.v[sl], self.step_count, self.hyper,
-                               grad_scale, mask, out)
+                               grad_scale, mask, out, dyn=self.dyn)
       return
     if self.kind == "sgd":
       sgd_reference(self.master[sl], grad_shard[sl], None if self.m is None else self.m[sl], self.hyper, grad_scale, out)

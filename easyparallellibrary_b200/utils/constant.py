@@ -26,7 +26,7 @@ GC_COLLECTION_NAME = "checkpoints"
 # are B200 extensions (flat-buffer sharding over NVSwitch makes them cheap).
 ZERO_LEVELS = ("", "v0", "v1", "v2", "v3")
 OFFLOAD_LEVELS = ("", "v0")
-AMP_LEVELS = ("", "o1", "bf16")
+AMP_LEVELS = ("", "o1", "bf16", "fp8")
 
 # broadcast / coalescing defaults (reference constant.py:81-82)
 SERIAL_COMM_MAX_SPLITS = 60

@@ -380,3 +380,75 @@ def test_rope_kernel():
   ref.backward(g.float())
   _close(qkv.grad, ref_in.grad, 2e-2, 3e-2, "rope bwd")
   assert torch.equal(out[:, :, 2], qkv[:, :, 2])          # V untouched
+
+
+def test_cuda_graph_step_matches_eager_step():
+  """The whole training step captured in a CUDA graph (parallel/graph_step.py) follows the eager trajectory: same kernels,
+  per-step optimizer values read from device memory; and it really replays (no eager launches after the capture)."""
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config
+  from easyparallellibrary_b200.ops import _lib
+  runs = {}
+  for graph in (False, True):
+    torch.manual_seed(0)
+    epl.init(epl.Config({"amp.level": "bf16"}))
+    with epl.replicate(1):
+      model = GPT2(GPT2Config.named("tiny"))
+    tr = epl.Trainer(model, "adamw", lr=1e-3, cuda_graph=graph)
+    g = torch.Generator().manual_seed(1)
+    toks = [torch.randint(0, 512, (8, 128), generator=g).to(DEV) for _ in range(8)]
+    runs[graph] = [tr.step(t, t).item() for t in toks]
+    if graph:
+      assert tr._graphed is not None and tr._graphed.graph is not None and not tr._graphed.failed
+      assert tr._graphed.launches_per_replay > 20
+      assert tr.optimizers[0][0].step_count == 8
+  for a, b in zip(runs[False], runs[True]):
+    assert abs(a - b) < 2e-3 * abs(a) + 1e-3, (runs[False], runs[True])
+
+
+def test_fp8_quantize_and_gemm():
+  """e4m3 path: the quantiser against torch's float8_e4m3fn cast, the UTCQMMA GEMM against an fp32 matmul of the SAME quantised
+  operands (tight: only accumulation order and the bf16 output rounding differ) and against the unquantised product (loose: e4m3
+  has 3 mantissa bits)."""
+  from easyparallellibrary_b200.ops import fp8
+  from easyparallellibrary_b200.ops import linear as L
+  torch.manual_seed(0)
+  x = (torch.randn(512, 768, device=DEV) * 2).bfloat16()
+  q, inv = fp8.quantize_e4m3(x)
+  amax = x.float().abs().max()
+  assert abs(inv.item() - amax.item() / 448.0) < 1e-6 * amax.item()
+  ref_q = (x.float() * (448.0 / amax)).to(torch.float8_e4m3fn)
+  assert torch.equal(q.view(torch.float8_e4m3fn).float(), ref_q.float())
+  for (M, N, K) in ((512, 768, 1024), (1024, 1600, 1600), (300, 520, 272)):
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    b = torch.randn(N, device=DEV).bfloat16()
+    y = fp8.gemm_fp8(a, w, bias=b, epilogue=L.EPI_BIAS)
+    aq, sa = fp8.quantize_e4m3(a)
+    wq, sw = fp8.quantize_e4m3(w)
+    exact = (aq.view(torch.float8_e4m3fn).float() @ wq.view(torch.float8_e4m3fn).float().t()) * (sa * sw) + b.float()
+    full = a.float() @ w.float().t() + b.float()
+    scale = full.abs().max().item()
+    assert (y.float() - exact).abs().max().item() < 8e-3 * scale, (M, N, K)
+    assert (y.float() - full).abs().max().item() < 0.08 * scale, (M, N, K)
+
+
+def test_fp8_training_follows_bf16():
+  """amp.level = fp8 (forward GEMMs in e4m3, backward bf16): same loss curve as bf16 within a few percent over 40 steps."""
+  import easyparallellibrary_b200 as epl
+  from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config
+  curves = {}
+  for level in ("bf16", "fp8"):
+    torch.manual_seed(0)
+    epl.init(epl.Config({"amp.level": level}))
+    with epl.replicate(1):
+      model = GPT2(GPT2Config(vocab_size=2048, n_positions=128, n_embd=512, n_layer=2, n_head=8))
+    tr = epl.Trainer(model, "adamw", lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    toks = torch.randint(0, 2048, (8, 128), generator=g).to(DEV)
+    curves[level] = [tr.step(toks, toks).item() for _ in range(40)]
+  from easyparallellibrary_b200.ops import fp8
+  fp8.ENABLED = False
+  assert curves["fp8"][-1] < 0.7 * curves["fp8"][0]
+  for a, b in zip(curves["bf16"], curves["fp8"]):
+    assert abs(a - b) < 0.05 * abs(a) + 0.05, (curves["bf16"][::8], curves["fp8"][::8])

@@ -49,6 +49,25 @@ def main():
       L._FORCE_BN = 0
       t = timeit(ref)
       rows.append((name, layout, "cublas", t, fl / t / 1e9))
+  # fp8 (e4m3) forward GEMMs: kernel only (operands pre-quantised) and including both per-tensor quantisation passes
+  from easyparallellibrary_b200.ops import fp8, _lib
+  lib = _lib.require()
+  for name, M, N, K in shapes:
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    xq, sx = fp8.quantize_e4m3(x)
+    wq, sw = fp8.quantize_e4m3(w)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    fl = 2.0 * M * N * K
+
+    def kern():
+      rc = lib.epl_gemm_fp8(xq.data_ptr(), wq.data_ptr(), out.data_ptr(), M, N, K, K, K, N, None, None, None, 0, _lib.dtype_code(out.dtype),
+                            1.0, sx.data_ptr(), sw.data_ptr(), 0, _lib.stream())
+      assert rc == 0
+    t = timeit(kern)
+    rows.append((name, "nt fwd", "fp8", t, fl / t / 1e9))
+    t = timeit(lambda: fp8.gemm_fp8(x, w, b_q=(wq, sw)))
+    rows.append((name, "nt fwd", "fp8+qx", t, fl / t / 1e9))
   for r in rows:
     print("%-8s %-7s bn=%-6s %8.3f ms %8.1f TFLOP/s" % r)
   json.dump(rows, open("gpurun_out/gemm_bench.json", "w"))

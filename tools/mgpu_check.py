@@ -417,28 +417,80 @@ def check_moe(dev, world, rank):
   moe.USE_P2P_KERNEL = True
 
 
+def check_clip(dev, world, rank):
+  """K1 with gradient clipping (clip-then-reduce: the local coefficient is applied to the bucket before the kernel reads it)
+  vs the NCCL + separate optimizer path with the same clipping."""
+  res = {}
+  for fused in (False, True):
+    from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config
+    epl.init(epl.Config({"amp.level": "bf16", "communication.fused_kernels": fused}))
+    torch.manual_seed(0)
+    with epl.replicate(1):
+      cfg = GPT2Config.named("tiny", n_embd=256, n_head=4, vocab_size=2048)
+      model = GPT2(cfg)
+    tr = epl.Trainer(model, "adamw", lr=1e-2, eps=1.0, max_grad_norm=0.05).build()
+    assert (tr.fused is not None) == fused
+    g = torch.Generator().manual_seed(100 + rank)
+    out = None
+    for _ in range(4):
+      t = torch.randint(0, cfg.vocab_size, (4, 128), generator=g).to(dev)
+      out = tr.step(t, t)
+    torch.cuda.synchronize()
+    res[fused] = (torch.cat([b.flat_param.float().flatten() for b in tr.flats[0].buckets]).clone(), float(out.grad_norm), out.item())
+  diff = (res[True][0] - res[False][0]).abs().max().item()
+  log("clip: fused vs NCCL path: max |dparam| = %.3e, grad norm %.4f vs %.4f, loss %.4f vs %.4f" % (
+      diff, res[True][1], res[False][1], res[True][2], res[False][2]))
+  assert res[True][1] > 0.05 and diff < 8e-3 and abs(res[True][2] - res[False][2]) < 0.03
+
+
+def check_zero3(dev, world, rank):
+  """ZeRO-3 (+ prefetch, + recompute, + weight/optimizer offload) on GPUs vs plain data parallelism: same trajectory, and the
+  persistent device bytes the engine reports are what the allocator holds between steps."""
+  from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config
+  res = {}
+  for name, conf in (("dp", {"communication.fused_kernels": False}), ("zero3", {"zero.level": "v3"}),
+                     ("zero3+gc+offload", {"zero.level": "v3", "gradient_checkpoint.type": "auto", "offload.level": "v0"})):
+    conf = dict(conf)
+    conf["amp.level"] = "bf16"
+    epl.init(epl.Config(conf))
+    torch.manual_seed(0)
+    with epl.replicate(1):
+      cfg = GPT2Config.named("tiny", n_embd=256, n_head=4, vocab_size=2048, n_layer=4)
+      model = GPT2(cfg)
+    tr = epl.Trainer(model, "adamw", lr=1e-2, eps=1.0).build()
+    g = torch.Generator().manual_seed(100 + rank)
+    losses = []
+    for _ in range(4):
+      t = torch.randint(0, cfg.vocab_size, (4, 128), generator=g).to(dev)
+      losses.append(tr.step(t, t).item())
+    torch.cuda.synchronize()
+    res[name] = losses
+    if tr.zero3:
+      z = next(iter(tr.zero3.values()))
+      log("  %s: persistent device bytes per rank %.2f MB (model %.2f M params), units %d, prefetch %s" % (
+          name, z.persistent_bytes() / 1e6, cfg.num_params / 1e6, len(z.units), z.prefetch))
+    del tr, model
+  log("zero3: losses dp %s | zero3 %s | zero3+gc+offload %s" % tuple([round(v, 4) for v in res[k]] for k in ("dp", "zero3", "zero3+gc+offload")))
+  for k in ("zero3", "zero3+gc+offload"):
+    assert max(abs(a - b) for a, b in zip(res["dp"], res[k])) < 0.03, (k, res)
+
+
 def main():
   dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
   rank, world = dist.get_rank(), dist.get_world_size()
   dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
   torch.cuda.set_device(dev)
   what = sys.argv[1:] or ["native", "symm", "fused"]
-  if "native" in what:
-    check_native(dev, world, rank)
-  if "symm" in what:
-    check_symm(dev, world, rank)
-  if "fused" in what:
-    check_fused(dev, world, rank)
-  if "k1" in what:
-    check_k1(dev, world, rank)
-  if "k1bench" in what:
-    bench_k1(dev, world, rank)
-  if "tp" in what:
-    check_tp(dev, world, rank)
-  if "tptrain" in what:
-    check_tp_train(dev, world, rank)
-  if "moe" in what:
-    check_moe(dev, world, rank)
+  table = [("native", check_native), ("symm", check_symm), ("k1", check_k1), ("k1bench", bench_k1), ("fused", check_fused),
+           ("clip", check_clip), ("tp", check_tp), ("tptrain", check_tp_train), ("moe", check_moe), ("zero3", check_zero3)]
+  if "all" in what:
+    what = [n for n, _ in table if n != "k1bench"]
+  for name, fn in table:
+    if name in what:
+      fn(dev, world, rank)
+      torch.cuda.synchronize()
+      dist.barrier()
+      log("CHECK %s PASSED (world %d)" % (name, world))
   dist.barrier()
   log("MGPU CHECK PASSED")
   dist.destroy_process_group()

@@ -188,7 +188,8 @@ class BertWorkload(Workload):
     torch.manual_seed(1234)
     with torch.device(dev):
       model = Bert(cfg)
-    self.trainer = epl.Trainer(model, "adamw", lr=1e-4, weight_decay=0.01, baseline=(args.impl == "baseline" and tp == 1)).build()
+    self.trainer = epl.Trainer(model, "adamw", lr=1e-4, weight_decay=0.01, baseline=(args.impl == "baseline" and tp == 1),
+                               cuda_graph=(not args.no_graph and args.impl != "baseline")).build()
     groups = world // tp if tp > 1 else self.trainer.plan.num_replicas
     self.replicas = groups
     B = batch * (M if stages > 1 else 1)
@@ -241,7 +242,7 @@ class ResNetWorkload(Workload):
       with torch.device(dev):
         with epl.replicate(device_count=1):
           model = ResNet50(num_classes=classes)
-      self.trainer = epl.Trainer(model, "adamw", lr=1e-4, weight_decay=0.01).build()
+      self.trainer = epl.Trainer(model, "adamw", lr=1e-4, weight_decay=0.01, cuda_graph=not args.no_graph).build()
       self.replicas = self.trainer.plan.num_replicas
     gen = torch.Generator(device="cpu").manual_seed(rank)
     self.host = [(torch.randn(batch, 3, 224, 224, generator=gen).bfloat16().pin_memory(),

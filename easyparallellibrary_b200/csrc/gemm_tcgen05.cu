@@ -65,7 +65,9 @@ constexpr int kMaxPeers = 8;
 enum CommMode : int { COMM_NONE = 0, COMM_AG = 1, COMM_RS = 2, COMM_AGB = 3 };   // AGB: the gathered operand is B (ZeRO-3 weights)
 struct CommParams {
   int rank, world;
-  uint32_t epoch;              // strictly increasing per launch on this workspace
+  uint32_t epoch;              // strictly increasing per launch on this workspace; 0 = read it from local_sync[31] (+1): the launch
+                               // then carries no per-call host value and can be replayed from a CUDA graph (a one-thread
+                               // kernel launched right after bumps the stored epoch, see epl_gemm_fused)
   int copy_ctas;               // mode 1: trailing CTAs of the grid that run the NVLink copy role
   int rows_per_rank;           // rows of the gathered operand owned by each rank (M / world, or N / world for COMM_AGB)
   uint32_t* flags[kMaxPeers];  // symmetric signal pad of every rank: [0,8) start slots, [8,16) end slots
@@ -260,7 +262,11 @@ EPL_DEVICE void ag_copy_role(const GemmParams& p, const CommParams& c, int gemm_
 template <int BN, int kComm>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const GemmParams p, const CommParams c) {
+                    const GemmParams p, const CommParams c_in) {
+  CommParams c = c_in;
+  if constexpr (kComm != COMM_NONE) {
+    if (c.epoch == 0) c.epoch = *reinterpret_cast<volatile uint32_t*>(c.local_sync + 31) + 1u;
+  }
   using L = SmemLayout<BN>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -1207,6 +1213,8 @@ extern "C" int epl_gemm_fp8(const void* A, const void* B, void* D, int M, int N,
   return launch_gemm2(ma, mb, p, sms, (cudaStream_t)stream);
 }
 
+__global__ void bump_epoch_kernel(uint32_t* word) { *word = *word + 1u; }
+
 // Fused tensor-parallel GEMMs.  mode 1 (all-gather -> GEMM): A is the local gathered buffer `ag_dst` [M, K] which the
 // kernel's copy CTAs fill from `ag_src[r]` (each [M/world, K], contiguous).  mode 2 (GEMM -> reduce-scatter): the tiles are
 // written to `rs_stage[owner]` slot `rank`, then reduced into `rs_out` [M/world, ldd] (bf16 only).
@@ -1237,23 +1245,26 @@ extern "C" int epl_gemm_fused(int mode, const void* A, const void* B, int M, int
     c.rs_stage[i] = rs_stage ? rs_stage[i] : nullptr;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  int rc2 = -22;
   if (mode == COMM_AG) {
     if (lda != K || (K % 8)) return -21;
-    if (bn == 256) return launch_gemm<256, COMM_AG>(ma, mb, p, c, kNumSMs, st);
-    if (bn == 160) return launch_gemm<160, COMM_AG>(ma, mb, p, c, kNumSMs, st);
-    return launch_gemm<128, COMM_AG>(ma, mb, p, c, kNumSMs, st);
-  }
-  if (mode == COMM_AGB) {
+    if (bn == 256) rc2 = launch_gemm<256, COMM_AG>(ma, mb, p, c, kNumSMs, st);
+    else if (bn == 160) rc2 = launch_gemm<160, COMM_AG>(ma, mb, p, c, kNumSMs, st);
+    else rc2 = launch_gemm<128, COMM_AG>(ma, mb, p, c, kNumSMs, st);
+  } else if (mode == COMM_AGB) {
     if (b_mn_major || ldb != K || (K % 8)) return -21;
-    if (bn == 256) return launch_gemm<256, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
-    if (bn == 160) return launch_gemm<160, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
-    return launch_gemm<128, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
-  }
-  if (mode == COMM_RS) {
+    if (bn == 256) rc2 = launch_gemm<256, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
+    else if (bn == 160) rc2 = launch_gemm<160, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
+    else rc2 = launch_gemm<128, COMM_AGB>(ma, mb, p, c, kNumSMs, st);
+  } else if (mode == COMM_RS) {
     if (is_fp16 || (N % 8) || (ldd % 8)) return -21;
-    if (bn == 256) return launch_gemm<256, COMM_RS>(ma, mb, p, c, kNumSMs, st);
-    if (bn == 160) return launch_gemm<160, COMM_RS>(ma, mb, p, c, kNumSMs, st);
-    return launch_gemm<128, COMM_RS>(ma, mb, p, c, kNumSMs, st);
+    if (bn == 256) rc2 = launch_gemm<256, COMM_RS>(ma, mb, p, c, kNumSMs, st);
+    else if (bn == 160) rc2 = launch_gemm<160, COMM_RS>(ma, mb, p, c, kNumSMs, st);
+    else rc2 = launch_gemm<128, COMM_RS>(ma, mb, p, c, kNumSMs, st);
   }
-  return -22;
+  if (rc2 == 0 && epoch == 0) {                    // device-side epoch: advance it once the whole grid has finished
+    bump_epoch_kernel<<<1, 1, 0, st>>>(c.local_sync + 31);
+    rc2 = EPL_CHECK_LAUNCH();
+  }
+  return rc2;
 }

@@ -499,7 +499,11 @@ struct A2AArgs {
   uint32_t epoch;
 };
 
-__global__ void __launch_bounds__(512) alltoall_p2p_kernel(const A2AArgs a) {
+__global__ void a2a_bump_epoch_kernel(uint32_t* word) { *word = *word + 1u; }
+
+__global__ void __launch_bounds__(512) alltoall_p2p_kernel(const A2AArgs a_in) {
+  A2AArgs a = a_in;            // epoch 0: kept on the device (local_sync[3] = epoch of the previous call), graph-replayable
+  if (a.epoch == 0) a.epoch = *reinterpret_cast<volatile uint32_t*>(a.local_sync + 3) + 1u;
   // start: every peer has finished consuming its receive buffer from the previous call
   if (blockIdx.x == 0) {
     if (threadIdx.x < a.world) {
@@ -555,6 +559,7 @@ extern "C" int epl_alltoall_p2p(const void* send, void* const* recv_ptrs, void* 
   a.rank = rank; a.world = world; a.epoch = epoch;
   if (blocks <= 0) blocks = 64;
   epl::alltoall_p2p_kernel<<<std::min(blocks, epl::kNumSMs), 512, 0, (cudaStream_t)stream>>>(a);
+  if (epoch == 0) epl::a2a_bump_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint32_t*)local_sync + 3);
   return EPL_CHECK_LAUNCH();
 }
 
@@ -578,7 +583,9 @@ struct A2AGatherArgs {
   uint32_t epoch;
 };
 
-__global__ void __launch_bounds__(512) alltoall_gather_p2p_kernel(const A2AGatherArgs a) {
+__global__ void __launch_bounds__(512) alltoall_gather_p2p_kernel(const A2AGatherArgs a_in) {
+  A2AGatherArgs a = a_in;
+  if (a.epoch == 0) a.epoch = *reinterpret_cast<volatile uint32_t*>(a.local_sync + 3) + 1u;
   if (blockIdx.x == 0) {
     if (threadIdx.x < a.world) {
       __threadfence_system();
@@ -637,5 +644,90 @@ extern "C" int epl_alltoall_gather_p2p(const void* x, const void* index, void* c
   a.E = E; a.C = C; a.e_local = E / world; a.rank = rank; a.world = world; a.epoch = epoch;
   if (blocks <= 0) blocks = 64;
   epl::alltoall_gather_p2p_kernel<<<std::min(blocks, epl::kNumSMs), 512, 0, (cudaStream_t)stream>>>(a);
+  if (epoch == 0) epl::a2a_bump_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint32_t*)local_sync + 3);
+  return EPL_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NVLS — in-switch reduction through a multicast mapping (cuMulticastCreate / cuMulticastBindMem; the mapping is set up by
+// runtime/nvls.py).  One-shot all-reduce: after a flag barrier every rank owns 1/W of the buffer; for its slice it issues
+// multimem.ld_reduce (the NVSwitch adds the W copies and returns ONE value: (W-1)/W fewer bytes into the GPU than W peer
+// loads) and multimem.st (one store, the switch broadcasts it to all W copies).  bf16 inputs accumulate in fp32 inside the
+// switch (.acc::f32).
+// ---------------------------------------------------------------------------------------------------------
+namespace epl {
+struct NvlsArgs {
+  void* mc;                 // multicast address of the symmetric buffer
+  PeerTable flags;
+  uint32_t* local_sync;
+  int64_t nvec;             // 16-byte vectors in the buffer
+  int rank, world;
+  uint32_t epoch;
+};
+
+template <int kDtype>   // EPL_BF16 or EPL_F32
+__global__ void __launch_bounds__(512) nvls_allreduce_kernel(const NvlsArgs a_in) {
+  NvlsArgs a = a_in;
+  if (a.epoch == 0) a.epoch = *reinterpret_cast<volatile uint32_t*>(a.local_sync + 3) + 1u;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + a.rank, a.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + threadIdx.x) < a.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.local_sync), "r"(a.epoch) : "memory"); }
+  } else if (threadIdx.x == 0) {
+    uint32_t v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.local_sync) : "memory"); } while (v < a.epoch);
+  }
+  __syncthreads();
+  const int64_t per = (a.nvec + a.world - 1) / a.world;
+  const int64_t lo = per * a.rank, hi = min(lo + per, a.nvec);
+  int4* base = reinterpret_cast<int4*>(a.mc);
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t r0, r1, r2, r3;
+    if constexpr (kDtype == EPL_BF16) {
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(base + i) : "memory");
+      asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" :: "l"(base + i), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+    } else {
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(base + i) : "memory");
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(base + i), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+    }
+  }
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + kMaxPeers + a.rank, a.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + kMaxPeers + threadIdx.x) < a.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { a.local_sync[1] = 0u; __threadfence(); }
+  }
+}
+}  // namespace epl
+
+extern "C" int epl_nvls_allreduce(void* mc_ptr, void* const* flag_ptrs, void* local_sync, int64_t nbytes, int dtype, int rank, int world,
+                                  unsigned epoch, int blocks, void* stream) {
+  if (world > epl::kMaxPeers || (nbytes & 15)) return -20;
+  epl::NvlsArgs a;
+  for (int i = 0; i < epl::kMaxPeers; ++i) a.flags.ptr[i] = i < world ? flag_ptrs[i] : nullptr;
+  a.mc = mc_ptr; a.local_sync = (uint32_t*)local_sync; a.nvec = nbytes / 16; a.rank = rank; a.world = world; a.epoch = epoch;
+  if (blocks <= 0) blocks = 32;
+  blocks = std::min(blocks, epl::kNumSMs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == EPL_BF16) epl::nvls_allreduce_kernel<EPL_BF16><<<blocks, 512, 0, st>>>(a);
+  else if (dtype == EPL_F32) epl::nvls_allreduce_kernel<EPL_F32><<<blocks, 512, 0, st>>>(a);
+  else return -1;
+  if (epoch == 0) epl::a2a_bump_epoch_kernel<<<1, 1, 0, st>>>((uint32_t*)local_sync + 3);
   return EPL_CHECK_LAUNCH();
 }

@@ -24,6 +24,17 @@ class ModelPhase(enum.Enum):
 
 
 _tls = threading.local()
+_listeners = []          # callables (phase, "enter" | "exit"): profilers sample at phase boundaries (profiler/memory.py)
+
+
+def add_phase_listener(fn) -> None:
+  if fn not in _listeners:
+    _listeners.append(fn)
+
+
+def remove_phase_listener(fn) -> None:
+  if fn in _listeners:
+    _listeners.remove(fn)
 
 
 def current_phase() -> ModelPhase:
@@ -38,9 +49,13 @@ class _PhaseScope(object):
   def __enter__(self):
     self._prev = current_phase()
     _tls.phase = self._phase
+    for fn in _listeners:
+      fn(self._phase, "enter")
     return self._phase
 
   def __exit__(self, *exc):
+    for fn in _listeners:
+      fn(self._phase, "exit")
     _tls.phase = self._prev
     return False
 

@@ -23,7 +23,7 @@ class Bottleneck(nn.Module):
     self.bn2 = nn.BatchNorm2d(planes)
     self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
     self.bn3 = nn.BatchNorm2d(planes * 4)
-    self.relu = nn.ReLU(inplace=True)
+    self.relu = nn.ReLU()
     self.downsample = downsample
 
   def forward(self, x):
@@ -38,7 +38,7 @@ class ResNet50Backbone(nn.Module):
   def __init__(self, width: int = 64, layers=(3, 4, 6, 3)):
     super().__init__()
     self.inplanes = width
-    self.stem = nn.Sequential(nn.Conv2d(3, width, 7, 2, 3, bias=False), nn.BatchNorm2d(width), nn.ReLU(inplace=True),
+    self.stem = nn.Sequential(nn.Conv2d(3, width, 7, 2, 3, bias=False), nn.BatchNorm2d(width), nn.ReLU(),
                               nn.MaxPool2d(3, 2, 1))
     self.layer1 = self._make(width, layers[0], 1)
     self.layer2 = self._make(width * 2, layers[1], 2)

@@ -68,9 +68,8 @@ def _p2p_all_to_all(t: torch.Tensor, group) -> torch.Tensor:
   nbytes = t.numel() * t.element_size()
   seg = nbytes // group.size
   buf = ws.recv_buffer(nbytes)
-  ws.epoch += 1
   rc = lib.epl_alltoall_p2p(t.data_ptr(), buf.peer_table(0), ws.pad.slot_table(0), ws.sync.data_ptr(), seg, group.rank, group.size,
-                            ws.epoch, 64, _lib.stream())
+                            0, 64, _lib.stream())                     # epoch 0: the kernels keep it on the device (graph-replayable)
   _lib.check(rc, "alltoall_p2p")
   return buf.tensor(t.dtype, t.numel()).view(t.shape).clone()
 
@@ -121,9 +120,8 @@ def _p2p_dispatch(x2: torch.Tensor, index: torch.Tensor, E: int, slots: int, gro
   e_local = E // group.size
   nbytes = group.size * e_local * slots * M * x2.element_size()
   buf = ws.recv_buffer(nbytes)
-  ws.epoch += 1
   rc = lib.epl_alltoall_gather_p2p(x2.data_ptr(), index.data_ptr(), buf.peer_table(0), ws.pad.slot_table(0), ws.sync.data_ptr(),
-                                   M * x2.element_size(), E, slots, group.rank, group.size, ws.epoch, 96, _lib.stream())
+                                   M * x2.element_size(), E, slots, group.rank, group.size, 0, 96, _lib.stream())
   _lib.check(rc, "alltoall_gather_p2p")
   return buf.tensor(x2.dtype, group.size * e_local * slots * M).view(e_local, group.size * slots, M).clone()
 

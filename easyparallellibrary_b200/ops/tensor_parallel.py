@@ -164,9 +164,17 @@ class DistributedDense(nn.Module):
 
   def forward(self, x: torch.Tensor) -> torch.Tensor:
     from easyparallellibrary_b200.ops.linear import linear
-    if self.gather_input:
-      x = self.bridge(x)
-    y = linear(x, self.weight, self.bias)
+    from easyparallellibrary_b200.ops import tp_fused
+    g = self.group
+    if (self.gather_input and g.size > 1 and x.dim() == 2 and x.is_contiguous() and tp_fused._fused_ok(x, g)
+        and self.weight.dtype == x.dtype and x.shape[1] % 8 == 0 and self.weight.shape[0] % 8 == 0):
+      # the bridge's all-gather and the GEMM are ONE kernel (K3a: copy CTAs pull the peers' batch shards over NVLink while the
+      # tcgen05 tiles whose rows have landed are multiplied); its backward is the fused GEMM -> reduce-scatter (K3b)
+      y = tp_fused.all_gather_linear(x, self.weight, self.bias, g)
+    else:
+      if self.gather_input:
+        x = self.bridge(x)
+      y = linear(x, self.weight, self.bias)
     y.epl_shard_start = self.start
     return self.activation(y) if self.activation is not None else y
 

@@ -46,8 +46,8 @@ class TPWorkspace(object):
     self.pg = pg
     self.pad_ag = SignalPad(1, group.ranks, device, group=pg)
     self.pad_rs = SignalPad(1, group.ranks, device, group=pg)
-    self.sync_ag = torch.zeros(16, dtype=torch.int32, device=device)
-    self.sync_rs = torch.zeros(16, dtype=torch.int32, device=device)
+    self.sync_ag = torch.zeros(32, dtype=torch.int32, device=device)
+    self.sync_rs = torch.zeros(32, dtype=torch.int32, device=device)
     self.epoch_ag = 0
     self.epoch_rs = 0
     self.shard: Optional[SymmetricBuffer] = None
@@ -89,9 +89,8 @@ def ag_gemm(x_shard2: torch.Tensor, w: torch.Tensor, group, bias=None, gelu: boo
   y = torch.empty((M, N), dtype=x_shard2.dtype, device=x_shard2.device)
   pre = torch.empty_like(y) if gelu else None
   epi = L.EPI_BIAS_GELU if gelu else (L.EPI_BIAS if bias is not None else L.EPI_NONE)
-  ws.epoch_ag += 1
   rc = lib.epl_gemm_fused(1, x_full.data_ptr(), w.data_ptr(), M, N, K, K, w.stride(0), N, int(b_mn_major), _lib.ptr(bias),
-                          _lib.ptr(pre), epi, y.data_ptr(), group.rank, group.size, ws.epoch_ag, COPY_CTAS,
+                          _lib.ptr(pre), epi, y.data_ptr(), group.rank, group.size, 0, COPY_CTAS,      # epoch 0: kept on the device
                           ws.pad_ag.slot_table(0), ws.sync_ag.data_ptr(), src.peer_table(0), None, None,
                           int(x_shard2.dtype == torch.float16), _lib.stream())
   _lib.check(rc, "ag_gemm")
@@ -107,9 +106,8 @@ def gemm_rs(a: torch.Tensor, w: torch.Tensor, group, b_mn_major: bool = False) -
   rows = M // group.size
   stage = ws.stage_buffer(group.size * rows * N * 2)
   out = torch.empty((rows, N), dtype=a.dtype, device=a.device)
-  ws.epoch_rs += 1
   rc = lib.epl_gemm_fused(2, a.data_ptr(), w.data_ptr(), M, N, K, a.stride(0), w.stride(0), N, int(b_mn_major), None, None, 0,
-                          None, group.rank, group.size, ws.epoch_rs, 0, ws.pad_rs.slot_table(0), ws.sync_rs.data_ptr(), None,
+                          None, group.rank, group.size, 0, 0, ws.pad_rs.slot_table(0), ws.sync_rs.data_ptr(), None,
                           stage.peer_table(0), out.data_ptr(), 0, _lib.stream())
   _lib.check(rc, "gemm_rs")
   return out
@@ -127,7 +125,7 @@ def ag_weight_gemm(x2: torch.Tensor, w_shard: torch.Tensor, group, bias=None, ge
   ws = workspace(group, x2.device)
   if not hasattr(ws, "pad_agb"):
     ws.pad_agb = SignalPad(1, group.ranks, x2.device, group=ws.pg)
-    ws.sync_agb = torch.zeros(16, dtype=torch.int32, device=x2.device)
+    ws.sync_agb = torch.zeros(32, dtype=torch.int32, device=x2.device)
     ws.epoch_agb = 0
     ws.wshard = None
   rows, K = w_shard.shape
@@ -148,9 +146,8 @@ def ag_weight_gemm(x2: torch.Tensor, w_shard: torch.Tensor, group, bias=None, ge
   y = torch.empty((M, N), dtype=x2.dtype, device=x2.device)
   pre = torch.empty_like(y) if gelu else None
   epi = L.EPI_BIAS_GELU if gelu else (L.EPI_BIAS if bias is not None else L.EPI_NONE)
-  ws.epoch_agb += 1
   rc = lib.epl_gemm_fused(3, x2.data_ptr(), w_full.data_ptr(), M, N, K, x2.stride(0), K, N, 0, _lib.ptr(bias), _lib.ptr(pre), epi,
-                          y.data_ptr(), group.rank, group.size, ws.epoch_agb, COPY_CTAS, ws.pad_agb.slot_table(0),
+                          y.data_ptr(), group.rank, group.size, 0, COPY_CTAS, ws.pad_agb.slot_table(0),
                           ws.sync_agb.data_ptr(), ws.wshard.peer_table(0), None, None, int(x2.dtype == torch.float16), _lib.stream())
   _lib.check(rc, "ag_weight_gemm")
   return y, pre, w_full

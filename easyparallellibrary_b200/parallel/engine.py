@@ -735,7 +735,7 @@ class Trainer(object):
       return max(self.plan.world // max(self._split_size, 1), 1)
     return comm.size
 
-  def _apply_group(self, s: int, mean: bool, scale0: float) -> None:
+  def _apply_group(self, s: int, mean: bool, scale0: float, only: Optional[Sequence[int]] = None) -> None:
     cfg = self.config
     comm, flat, opts = self.dp_comms[s], self.flats[s], self.optimizers[s]
     sharded = self._sharded[s]
@@ -745,6 +745,8 @@ class Trainer(object):
     groups = max(1, cfg.optimizer.num_apply_group)
     gathers = []
     for b, opt in zip(flat.buckets, opts):
+      if only is not None and b.index not in only:
+        continue
       lo, hi = b.shard_range(comm.rank if sharded else 0, comm.size if sharded else 1)
       gshard, pshard = b.flat_grad[lo:hi], b.flat_param[lo:hi]
       if self.baseline:
@@ -760,16 +762,17 @@ class Trainer(object):
       if w is not None:
         w.wait()
 
-  def _apply_group_library(self, s: int, mean: bool) -> None:
-    """Reduce + apply one parameter group through the library path (used by the fused engine for groups that
-    do not live in symmetric memory, e.g. fp32 or single-replica groups)."""
+  def _apply_group_library(self, s: int, mean: bool, only: Optional[Sequence[int]] = None) -> None:
+    """Reduce + apply one parameter group (or the buckets ``only`` of it) through the library path: used by the fused engine
+    for what does not live in symmetric memory — fp32 buckets, single-replica groups."""
     for b in reversed(self.flats[s].buckets):
-      self._launch_bucket_reduce(s, b)
+      if only is None or b.index in only:
+        self._launch_bucket_reduce(s, b)
     for _, _, w in self._pending:
       if w is not None:
         w.wait()
     self._pending = []
-    self._apply_group(s, mean, self.scaler.inv_scale)
+    self._apply_group(s, mean, self.scaler.inv_scale, only=only)
 
   def _baseline_apply(self, opt: FlatOptimizer, g, p, scale) -> None:
     from easyparallellibrary_b200.runtime.optimizer import adamw_reference, sgd_reference
@@ -863,9 +866,10 @@ class Trainer(object):
     self.model.eval()
     Graph.get().current_micro_batch = batch
     try:
-      if self.plan.pipeline:
-        return self.pipe.forward_only(batch)
-      return self._forward_loss(batch, kwargs)
+      with amp_lib.o1_autocast(self.device.type, enabled=self.o1):       # same per-op precision (and stage-boundary dtypes) as training
+        if self.plan.pipeline:
+          return self.pipe.forward_only(batch)
+        return self._forward_loss(batch, kwargs)
     finally:
       self.model.train(was)
       for z in self.zero3.values():

@@ -52,10 +52,13 @@ class FusedDataParallel(object):
     self.kernel = os.environ.get("EPL_K1", "v2")      # "v1": the register-path kernel of round 1 (A/B measurements)
     self.overlap_blocks = int(os.environ.get("EPL_FUSED_OVERLAP_BLOCKS", "8"))
     self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "1") != "0" and self.kernel == "v2"
-    # Each rank's AdamW shard is 1/W of the model: with W = 2 the bucket kernels stream 14 B/param of optimizer state per
-    # rank and a handful of CTAs cannot keep up with backward (measured on 2 x B200: 149.9 ms/step overlapped on 8 CTAs vs
-    # 117.5 ms after backward); from W = 4 on the per-rank work is small enough.
-    self.overlap_min_world = int(os.environ.get("EPL_FUSED_OVERLAP_MIN_WORLD", "4"))
+    # Each rank's AdamW shard is 1/W of the model, so the bucket kernels' work per rank shrinks with W while their cost to the
+    # backward pass (8 SMs taken from every kernel that runs meanwhile + L2 traffic) does not.  Measured, GPT-2-XL, step ms
+    # overlapped vs after backward: W=2 149.9 vs 117.5 (eager), W=4 122.6 vs 120.7 (CUDA graph; exposed 5.1 vs 10.5 ms but
+    # forward+backward 7 ms slower).  At W=8 the per-rank work halves again and ~12 ms would be exposed otherwise: overlap
+    # from W = 8 on (EPL_FUSED_OVERLAP_MIN_WORLD overrides).
+    self.overlap_min_world = int(os.environ.get("EPL_FUSED_OVERLAP_MIN_WORLD", "8"))
+    self.reserve_sms = os.environ.get("EPL_FUSED_RESERVE", "1") != "0"    # shrink the GEMM grids by the bucket kernel's SMs while it may run
     self.launched = set()
     self._prepared = False
     self._reserved = False
@@ -81,7 +84,10 @@ class FusedDataParallel(object):
     need is launch-invariant).  Called once per step before the first bucket can become ready."""
     tr = self.trainer
     for s in self.pads:
-      comm, opts = tr.dp_comms[s], tr.optimizers[s]
+      comm = tr.dp_comms[s]
+      opts = [o for b, o in zip(tr.flats[s].buckets, tr.optimizers[s]) if self.handles(s, b)]
+      if not opts:
+        continue
       for o in opts:
         o.step_count += 1
       h, t = opts[0].hyper, opts[0].step_count
@@ -92,6 +98,11 @@ class FusedDataParallel(object):
       scale = tr.scaler.inv_scale / (tr.mean_divisor(s) if mean else 1)
       self.dyn[s].copy_(torch.tensor([h.lr, inv_c1, inv_c2, scale], dtype=torch.float32), non_blocking=True)
     self._prepared = True
+
+  def handles(self, s: int, b) -> bool:
+    """Buckets of 16-bit parameters live in symmetric memory and go through the fused kernel; fp32 buckets of the same group
+    (e.g. BatchNorm parameters kept in fp32 under bf16 AMP) take the library path."""
+    return s in self.pads and (s, "grad", b.dtype) in self.trainer._symm_buffers
 
   def reset_step(self) -> None:
     """Start of a step: forget per-step launch state (also after a step that was abandoned half-way, e.g. a failed capture)."""
@@ -107,9 +118,11 @@ class FusedDataParallel(object):
     are overwritten before every rank has finished the backward of the layers in this bucket."""
     if (s, bi) in self.launched or s not in self.pads or bi == 0:       # bucket 0 completes last: whole GPU, after backward
       return
+    if not self.handles(s, self.trainer.flats[s].buckets[bi]):
+      return
     if self.trainer.dp_comms[s].size < self.overlap_min_world:
       return
-    if not self._reserved:
+    if not self._reserved and self.reserve_sms:
       # leave the bucket kernel's TPCs out of the GEMM grids until the step's reduce phase is over (the GEMM would cope —
       # its tile scheduler is dynamic — but CTA pairs that start late only to find no work left lengthen each GEMM's tail)
       from easyparallellibrary_b200.ops import linear as L
@@ -162,9 +175,14 @@ class FusedDataParallel(object):
       if s not in self.pads:
         tr._apply_group_library(s, mean)
         continue
+      library = []
       for bi in range(len(tr.flats[s].buckets) - 1, -1, -1):
-        if (s, bi) not in self.launched:
+        if not self.handles(s, tr.flats[s].buckets[bi]):
+          library.append(bi)
+        elif (s, bi) not in self.launched:
           self.launch_bucket(s, bi)
+      if library:
+        tr._apply_group_library(s, mean, only=library)
     self.launched.clear()
     self._prepared = False
     return False, None

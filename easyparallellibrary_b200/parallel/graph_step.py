@@ -39,7 +39,11 @@ class GraphedStep(object):
     if cfg.gradient_checkpoint.check_gradients:
       return False
     multi = any(c.size > 1 for c in tr.dp_comms.values())
-    return (not multi) or (tr.fused is not None and all(s in tr.fused.pads or tr.dp_comms[s].size == 1 for s in tr.group_keys))
+    if not multi:
+      return True
+    # multi-rank: every bucket must go through the fused kernel (library collectives are not captured)
+    return tr.fused is not None and all(tr.dp_comms[s].size == 1 or all(tr.fused.handles(s, b) for b in tr.flats[s].buckets)
+                                        for s in tr.group_keys)
 
   def __init__(self, trainer):
     self.tr = trainer

@@ -325,7 +325,16 @@ class PipelineExecutor(object):
     tr._first_micro_batch, tr._last_micro_batch = True, False
     n_back = 0
     debug = bool(int(__import__("os").environ.get("EPL_PIPE_DEBUG", "0")))
+    timing = bool(int(__import__("os").environ.get("EPL_PIPE_TIMING", "0")))
+    import time as _time
+    host_t: Dict[str, float] = {}
+    t_prev = _time.perf_counter()
     for ins in self.program:
+      if timing:                                   # host time spent issuing each instruction kind (no device sync)
+        now = _time.perf_counter()
+        if getattr(self, "_last_op", None) is not None:
+          host_t[self._last_op] = host_t.get(self._last_op, 0.0) + (now - t_prev)
+        t_prev, self._last_op = now, ins.op
       if debug:
         print("[pipe rank %d stage %d] %r" % (tr.plan.rank, self.stage, ins), flush=True)
       if ins.op == S.RECV_F:
@@ -375,14 +384,24 @@ class PipelineExecutor(object):
         if not getattr(self, "_meta_sent", False):
           self._send_meta(y)
           self._meta_sent = True
-        sends.append(self.p2p.send_fwd(y.detach().contiguous()))
+        # graph mode: y is the static output buffer of a captured graph, overwritten by the instance's next replay -> send a copy
+        sends.append(self.p2p.send_fwd(y.detach().clone() if use_graphs else y.detach().contiguous()))
       elif ins.op == S.B:
         n_back += 1
         tr._last_micro_batch = n_back == self.M
         y = outputs.pop(ins.mb)
+        if timing and self.last:                   # split the last stage's backward into host-issue and device time
+          torch.cuda.synchronize(self.device)
+          _tb0 = _time.perf_counter()
         with phase_scope(ModelPhase.BACKWARD):
           if self.last:
             y.backward()
+            if timing:
+              _tb1 = _time.perf_counter()
+              torch.cuda.synchronize(self.device)
+              _tb2 = _time.perf_counter()
+              host_t["B_issue"] = host_t.get("B_issue", 0.0) + (_tb1 - _tb0)
+              host_t["B_device_after_issue"] = host_t.get("B_device_after_issue", 0.0) + (_tb2 - _tb1)
           else:
             g, req = recv_b.pop(ins.mb)
             req.wait()
@@ -390,8 +409,18 @@ class PipelineExecutor(object):
         tr._first_micro_batch = False
       elif ins.op == S.SEND_B:
         x = inputs.pop(ins.mb)
-        sends.append(self.p2p.send_bwd(x.grad.contiguous()))
+        sends.append(self.p2p.send_bwd(x.grad.clone() if use_graphs else x.grad.contiguous()))
       # REDUCE / APPLY are executed by the trainer after the program
+    if timing:
+      t_issue = _time.perf_counter()
+      torch.cuda.synchronize(self.device)
+      t_done = _time.perf_counter()
+      self._timing_rows = getattr(self, "_timing_rows", 0) + 1
+      if self._timing_rows in (3, 5):
+        print("[pipe timing rank %d stage %d graphs=%s] host issue per op (ms): %s | device tail after last issue %.1f ms" % (
+            tr.plan.rank, self.stage, bool(self.graphed), {str(k): round(v * 1e3, 1) for k, v in host_t.items()},
+            (t_done - t_issue) * 1e3), flush=True)
+      self._last_op = None
     for w in sends:
       w.wait()
     inputs.clear()

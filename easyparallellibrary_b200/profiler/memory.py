@@ -1,10 +1,11 @@
 """Memory profiling (reference ``epl/profiler/memory_profiler_hook.py:207-271``: per-device allocation
 timeline from RunMetadata, peak bytes, CSV + PNG with persistent / gradient / optimizer phases).
 
-Eager equivalent: the caching allocator's counters are sampled at phase boundaries of every profiled step
-(before step, after forward+backward, after optimizer apply); ``save()`` writes the CSV and — when
-matplotlib is importable — the phase-coloured PNG; ``snapshot()`` dumps the allocator history for
-``torch.cuda.memory._dump_snapshot`` style post-mortems.
+Eager equivalent: the caching allocator's counters are sampled at the phase boundaries of every profiled step — before the
+step (*persistent*: weights, gradient buckets, optimizer state), at the end of every forward (*forward*: + activations), of
+every backward (*backward*: gradients produced, activations freed) and of the apply phase (*apply*: optimizer temporaries) —
+through the engine's phase scopes (``ir/phase.py`` listeners); the peak counter is reset at each boundary, so every row also
+carries the peak *inside* its phase.  ``save()`` writes the CSV and — when matplotlib is importable — a PNG coloured by phase.
 """
 from __future__ import annotations
 
@@ -21,6 +22,20 @@ class MemoryProfilerHook(object):
     self.device = device
     self.rows: List[Dict[str, float]] = []
     self._step = 0
+    self._active = False
+    from easyparallellibrary_b200.ir import phase as phase_lib
+    self._phase_lib = phase_lib
+    phase_lib.add_phase_listener(self._on_phase)
+
+  def close(self) -> None:
+    self._phase_lib.remove_phase_listener(self._on_phase)
+
+  def _on_phase(self, phase, edge: str) -> None:
+    if not self._active or edge != "exit" or phase.value not in ("forward", "backward", "apply"):
+      return
+    self.rows.append(dict(step=self._step, phase=phase.value, **self._stats()))
+    if torch.cuda.is_available():
+      torch.cuda.reset_peak_memory_stats(self.device)
 
   def _stats(self) -> Dict[str, float]:
     if not torch.cuda.is_available():
@@ -29,7 +44,7 @@ class MemoryProfilerHook(object):
             "peak": float(torch.cuda.max_memory_allocated(self.device))}
 
   def before_step(self, trainer) -> None:
-    self._active = self._step % self.save_steps == 0 and len(self.rows) < 3 * self.max_steps
+    self._active = self._step % self.save_steps == 0 and len({r["step"] for r in self.rows}) < self.max_steps
     if self._active:
       if torch.cuda.is_available():
         torch.cuda.reset_peak_memory_stats(self.device)
@@ -38,7 +53,15 @@ class MemoryProfilerHook(object):
   def after_step(self, trainer, out) -> None:
     if self._active:
       self.rows.append(dict(step=self._step, phase="after_step", **self._stats()))
+    self._active = False
     self._step += 1
+
+  def phase_peaks(self) -> Dict[str, float]:
+    """Largest in-phase peak (bytes) per phase over the profiled steps."""
+    out: Dict[str, float] = {}
+    for r in self.rows:
+      out[r["phase"]] = max(out.get(r["phase"], 0.0), r["peak"])
+    return out
 
   @property
   def peak_bytes(self) -> float:

@@ -162,7 +162,8 @@ def save_checkpoint(trainer, directory: str, bucket_bytes: int = BUCKET_BYTES) -
       for s in trainer.plan.local_stages:
         for k, v in trainer.stage_modules[s].state_dict().items():
           state["stage%d.%s" % (s, k)] = v
-      files = builder.save(state, "model", {"global_step": trainer.global_step, "loss_scale": trainer.scaler.loss_scale})
+      files = builder.save(state, "model", {"global_step": trainer.global_step, "loss_scale": trainer.scaler.loss_scale,
+                                            "loss_scale_good_steps": int(getattr(trainer.scaler, "good_steps", 0))})
       if not sharded:
         builder.save(_optimizer_state(trainer), "optim")
   finally:
@@ -216,8 +217,31 @@ def load_checkpoint(trainer, directory: str) -> int:
       for i, u in enumerate(z.units):
         pre = "z%d.u%d." % (s, i)
         sds.append({k[len(pre):]: (int(v) if k.endswith(".step") else v) for k, v in opt.items() if k.startswith(pre)})
-      if all("shard_param" in sd for sd in sds):
+      if all("shard_param" in sd for sd in sds) and all(
+          sd["shard_param"].numel() == u.shard_numel for sd, u in zip(sds, z.units)):
         z.load_state_dict(sds)
+        restored.add(("zero3", s))
+    for s, z in zero3.items():
+      if ("zero3", s) in restored:
+        continue
+      # no shard state for this rank (checkpoint written without ZeRO-3, with another world size, or a rank directory is
+      # missing): rebuild the shards from the gathered model weights instead of silently keeping the initial values
+      prefix = "stage%d." % s
+      sd = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
+      names = {id(p): n for n, p in trainer.stage_modules[s].named_parameters()}
+      missing = [names.get(id(p), "?") for u in z.units for p in u.params if names.get(id(p)) not in sd]
+      if missing:
+        raise RuntimeError("checkpoint %s holds neither this rank's ZeRO-3 shards nor the full weights of %s" % (directory, missing[:5]))
+      for u in z.units:
+        full = torch.zeros(u.numel, dtype=u.dtype, device=u.device)
+        for p, o in zip(u.params, u.offsets):
+          src = sd[names[id(p)]]
+          full[o:o + src.numel()].copy_(src.reshape(-1).to(u.dtype))
+        lo = u.comm.rank * u.shard_numel
+        shard = full[lo:lo + u.shard_numel]
+        (u.shard_host if u.offload else u.shard_param).copy_(shard)
+        u.opt.master.copy_(shard.to(u.opt.master.dtype))           # moments restart at zero: the optimizer state was not in the checkpoint
+      restored.add(("zero3", s))
   # optimizers without restored state restart from the restored weights (fp32 master = parameters)
   for s in trainer.group_keys:
     comm, flat = trainer.dp_comms[s], trainer.flats[s]
@@ -229,4 +253,6 @@ def load_checkpoint(trainer, directory: str) -> int:
   trainer.global_step = int(extra.get("global_step", 0))
   if hasattr(trainer.scaler, "loss_scale") and "loss_scale" in extra:
     trainer.scaler.loss_scale = extra["loss_scale"]
+  if hasattr(trainer.scaler, "good_steps") and "loss_scale_good_steps" in extra:
+    trainer.scaler.good_steps = int(extra["loss_scale_good_steps"])
   return trainer.global_step

@@ -111,23 +111,36 @@ class SymmetricBuffer(object):
         self._imported.append(q.value)
 
   def tensor(self, dtype: torch.dtype, numel: int, byte_offset: int = 0) -> torch.Tensor:
-    nbytes = numel * torch.empty(0, dtype=dtype).element_size()
-    if byte_offset + nbytes > self.nbytes:
-      raise ValueError("view exceeds the symmetric buffer")
-    t = wrap_pointer(self.local_ptr + byte_offset, nbytes, dtype, self.device)
-    t._epl_symm_owner = self          # keep the allocation alive as long as a view exists
+    key = (dtype, numel, byte_offset)
+    views = self.__dict__.setdefault("_views", {})
+    t = views.get(key)                 # wrapping a raw pointer costs ~50 us of host time: the hot ops ask for the same views every call
+    if t is None:
+      nbytes = numel * torch.empty(0, dtype=dtype).element_size()
+      if byte_offset + nbytes > self.nbytes:
+        raise ValueError("view exceeds the symmetric buffer")
+      t = wrap_pointer(self.local_ptr + byte_offset, nbytes, dtype, self.device)
+      t._epl_symm_owner = self          # keep the allocation alive as long as a view exists
+      if len(views) < 64:
+        views[key] = t
     return t
 
   def peer_table(self, byte_offset: int = 0):
-    arr = (ctypes.c_void_p * 8)()
-    for r in range(self.world):
-      arr[r] = self.peer_ptrs[r] + byte_offset
+    tables = self.__dict__.setdefault("_tables", {})
+    arr = tables.get(byte_offset)
+    if arr is None:
+      arr = (ctypes.c_void_p * 8)()
+      for r in range(self.world):
+        arr[r] = self.peer_ptrs[r] + byte_offset
+      if len(tables) < 256:
+        tables[byte_offset] = arr
     return arr
 
   def close(self) -> None:
     for q in self._imported:
       self.lib.epl_symm_unimport(ctypes.c_void_p(q))
     self._imported = []
+    self.__dict__.pop("_views", None)
+    self.__dict__.pop("_tables", None)
     if self.local_ptr:
       self.lib.epl_symm_free(ctypes.c_void_p(self.local_ptr))
       self.local_ptr = 0

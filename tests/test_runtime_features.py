@@ -143,6 +143,10 @@ def test_profiler_hooks(tmp_path):
   s = fh.summary()
   assert s["tflops"] > 0 and 0 < s["median_step_s"]
   assert mh.save() and os.path.exists(os.path.join(tmp_path, "memory_timeline.csv"))
+  phases = [r["phase"] for r in mh.rows if r["step"] == 0]
+  assert phases == ["persistent", "forward", "backward", "apply", "after_step"]       # sampled at every phase boundary of the step
+  assert set(mh.phase_peaks()) == {"persistent", "forward", "backward", "apply", "after_step"}
+  mh.close()
   mem = profile_memory(tr)
   assert mem["weights"] == mem["gradients"] > 0 and mem["optimizer_state_device"] >= 2 * mem["weights"]
 

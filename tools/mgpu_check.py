@@ -475,6 +475,48 @@ def check_zero3(dev, world, rank):
     assert max(abs(a - b) for a, b in zip(res["dp"], res[k])) < 0.03, (k, res)
 
 
+def check_nvls(dev, world, rank):
+  """NVLS / multimem: in-switch all-reduce (csrc/symm.cu::nvls_allreduce_kernel) vs NCCL, values and time — when the platform
+  exposes multicast; otherwise the probe's verdict is reported and the check passes vacuously."""
+  from easyparallellibrary_b200.runtime import nvls
+  buf = nvls.probe(dev)
+  if buf is None or not buf.supported:
+    log("nvls: multicast NOT available on this platform (symmetric rendezvous %s) -> peer-pointer kernels remain the path" % (
+        "ok" if buf is not None else "failed"))
+    return
+  for dtype, n in ((torch.bfloat16, 1 << 16), (torch.float32, 1 << 14), (torch.bfloat16, 64 << 20)):
+    nb = n * (2 if dtype == torch.bfloat16 else 4)
+    big = nvls.MulticastBuffer(nb, dev) if nb > buf.nbytes else buf
+    t = big.tensor(dtype, n)
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    src = (torch.randn(n, device=dev, generator=gen) * 0.1).to(dtype)
+    ref = src.float().clone()
+    dist.all_reduce(ref)
+    t.copy_(src)
+    torch.cuda.synchronize(); dist.barrier()
+    big.all_reduce_(dtype, n, blocks=148 if nb > (1 << 22) else 16)
+    torch.cuda.synchronize(); dist.barrier()
+    err = (t.float() - ref).abs().max().item()
+    tol = 1e-6 if dtype == torch.float32 else 2e-2 * ref.abs().max().item()
+    times = {}
+    nccl_t = src.clone()
+    for name, fn in (("nvls", lambda: big.all_reduce_(dtype, n, blocks=148 if nb > (1 << 22) else 16)), ("nccl", lambda: dist.all_reduce(nccl_t))):
+      for _ in range(3):
+        fn()
+      torch.cuda.synchronize(); dist.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(10):
+        fn()
+      e1.record(); torch.cuda.synchronize()
+      tt = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      times[name] = tt.item()
+    log("nvls all-reduce %s x %d: max err %.2e ; multimem kernel %.4f ms vs NCCL %.4f ms (busbw %.0f GB/s)" % (
+        str(dtype).split(".")[-1], n, err, times["nvls"], times["nccl"], 2 * (world - 1) / world * nb / times["nvls"] / 1e6))
+    assert err <= tol, (err, tol)
+
+
 def main():
   dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
   rank, world = dist.get_rank(), dist.get_world_size()
@@ -482,7 +524,7 @@ def main():
   torch.cuda.set_device(dev)
   what = sys.argv[1:] or ["native", "symm", "fused"]
   table = [("native", check_native), ("symm", check_symm), ("k1", check_k1), ("k1bench", bench_k1), ("fused", check_fused),
-           ("clip", check_clip), ("tp", check_tp), ("tptrain", check_tp_train), ("moe", check_moe), ("zero3", check_zero3)]
+           ("clip", check_clip), ("tp", check_tp), ("tptrain", check_tp_train), ("moe", check_moe), ("zero3", check_zero3), ("nvls", check_nvls)]
   if "all" in what:
     what = [n for n, _ in table if n != "k1bench"]
   for name, fn in table:

@@ -141,6 +141,57 @@ class _StageFn(torch.nn.Module):
     return y
 
 
+class _GraphedStage(object):
+  """Forward and backward of one pipeline stage as two CUDA graphs with static input / output buffers.
+
+  Unlike ``torch.cuda.make_graphed_callables`` nothing goes through autograd at replay time: the backward graph ends with the
+  accumulation of every parameter gradient into the trainer's flat gradient buckets (weight-gradient GEMMs write there
+  directly, the other gradients are added by captured ``add_`` kernels), so an F or B instruction costs the host one small
+  copy and one graph launch — no per-parameter AccumulateGrad nodes, hooks or Python per micro-batch."""
+
+  def __init__(self, fn, x, labels, pool):
+    """Phase 1: capture the forward graph.  ALL forward graphs of a stage are captured before any backward graph, so that a
+    backward's temporaries can never be placed (by the shared pool) where another instance's saved activations live."""
+    self.fn = fn
+    self.x = x                                       # static input (requires_grad for stages > 0)
+    self.labels = tuple(labels)
+    self.pool = pool
+    self.g_fwd, self.g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self.g_fwd, pool=pool):
+      self.y = fn(self.x, *self.labels)              # keeps the autograd graph (and with it the saved activations) alive
+    self.y_out = self.y.detach()
+    self.gx = None
+
+  def capture_backward(self, grad_views, ones_grad: bool) -> None:
+    params = [p for p in self.fn.parameters() if p.requires_grad]
+    inputs = ([self.x] if self.x.requires_grad else []) + params
+    self.gy = torch.ones_like(self.y) if ones_grad else torch.zeros_like(self.y)
+    with torch.cuda.graph(self.g_bwd, pool=self.pool):
+      grads = torch.autograd.grad(outputs=(self.y,), inputs=tuple(inputs), grad_outputs=(self.gy,), allow_unused=True, retain_graph=True)
+      k = 0
+      if self.x.requires_grad:
+        self.gx = grads[0]
+        k = 1
+      for p, g in zip(params, grads[k:]):
+        if g is not None:
+          grad_views[id(p)].add_(g.view_as(grad_views[id(p)]))
+
+  def forward(self, x, labels):
+    if x.data_ptr() != self.x.data_ptr():
+      self.x.detach().copy_(x)
+    for s, l in zip(self.labels, labels):
+      if s.data_ptr() != l.data_ptr():
+        s.copy_(l)
+    self.g_fwd.replay()
+    return self.y_out
+
+  def backward(self, gy=None):
+    if gy is not None:
+      self.gy.copy_(gy)
+    self.g_bwd.replay()
+    return self.gx
+
+
 class PipelineExecutor(object):
   def __init__(self, trainer):
     self.tr = trainer
@@ -195,9 +246,9 @@ class PipelineExecutor(object):
     return max(1, min(self.M, self.num_stages - self.stage + (1 if "optimizer" in policy else 0)))
 
   def _build_graphs(self, micro: List[Tuple[Any, ...]]) -> None:
-    """Capture forward/backward graphs of this stage with ``torch.cuda.make_graphed_callables`` (static input/output buffers,
-    weight gradients of the GEMMs accumulate straight into the flat buckets inside the graph, the remaining parameter
-    gradients come back through autograd).  Any failure leaves the executor on the eager path."""
+    """Capture forward/backward CUDA graphs of this stage, one pair per micro-batch that can be in flight (``_GraphedStage``:
+    static input/output buffers, every parameter gradient accumulated into the flat buckets inside the backward graph).
+    Any failure leaves the executor on the eager path."""
     tr = self.tr
     k = self._in_flight()
     if k > 4:
@@ -210,13 +261,8 @@ class PipelineExecutor(object):
     if self.last and loss_fn is None:
       self.use_graphs = False
       return
-    fns = tuple(_StageFn(self.module, loss_fn, factor if self.last else 1.0) for _ in range(k))
-    if self.first:
-      x = mb[0].clone()
-    else:
-      x = torch.zeros(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
-      if x.is_floating_point():
-        x.requires_grad_()
+    fn = _StageFn(self.module, loss_fn, factor if self.last else 1.0)
+    self.stage_factor = fn.factor
     labels = tuple(t.clone() for t in mb[1:] if isinstance(t, torch.Tensor)) if self.last else ()
     if self.last and len(labels) != len(mb) - 1:
       self.use_graphs = False
@@ -226,9 +272,29 @@ class PipelineExecutor(object):
         p.epl_sink_fresh = False
     tr._first_micro_batch, tr._last_micro_batch = False, False
     Graph.get().current_micro_batch = mb
+    grad_views = {pid: v[0] for pid, v in tr._grad_view.items()}
+
+    def make_x():
+      if self.first:
+        return mb[0].clone()
+      x = torch.zeros(self._shape_fwd[0], dtype=self._shape_fwd[1], device=self.device)
+      return x.requires_grad_() if x.is_floating_point() else x
     try:
-      sample = tuple((x.detach().clone().requires_grad_(x.requires_grad),) + labels for _ in range(k))
-      self.graphed = list(torch.cuda.make_graphed_callables(fns, sample, num_warmup_iters=2, allow_unused_input=True))
+      # one eager pass on a side stream first (torch's capture recipe), then k (forward, backward) graph pairs in one pool
+      side = torch.cuda.Stream(device=self.device)
+      side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(side):
+        xw = make_x()
+        yw = fn(xw, *labels)
+        ins_w = ([xw] if xw.requires_grad else []) + [p for p in fn.parameters() if p.requires_grad]
+        torch.autograd.grad((yw,), tuple(ins_w), (torch.ones_like(yw),), allow_unused=True)
+        del xw, yw, ins_w
+      torch.cuda.current_stream().wait_stream(side)
+      torch.cuda.synchronize(self.device)
+      pool = torch.cuda.graph_pool_handle()
+      self.graphed = [_GraphedStage(fn, make_x(), tuple(l.clone() for l in labels), pool) for _ in range(k)]
+      for st in reversed(self.graphed):
+        st.capture_backward(grad_views, ones_grad=self.last)
     except Exception as e:      # pragma: no cover - depends on the CUDA runtime
       from easyparallellibrary_b200.utils.logging import get_logger
       get_logger().warning("pipeline stage %d: CUDA graph capture failed (%s); running the stage eagerly", self.stage, e)
@@ -319,6 +385,7 @@ class PipelineExecutor(object):
     outputs: Dict[int, torch.Tensor] = {}
     recv_f: Dict[int, Tuple[torch.Tensor, Any]] = {}
     recv_b: Dict[int, Tuple[torch.Tensor, Any]] = {}
+    grads_in: Dict[int, torch.Tensor] = {}          # graph mode: the static input-gradient buffer of each backward
     sends: List[Any] = []
     losses: List[torch.Tensor] = []
     collected = []
@@ -365,10 +432,10 @@ class PipelineExecutor(object):
             x.requires_grad_()
         with phase_scope(ModelPhase.FORWARD):
           if use_graphs:
-            fn = self.graphed[ins.mb % len(self.graphed)]
-            y = fn(x, *mb[1:]) if self.last else fn(x)
+            st = self.graphed[ins.mb % len(self.graphed)]
+            y = st.forward(x, mb[1:] if self.last else ())
             if self.last:
-              losses.append(y.detach() / fn.factor if fn.factor != 1.0 else y.detach().clone())
+              losses.append(y / self.stage_factor if self.stage_factor != 1.0 else y.clone())
           else:
             y = self.module(x)
             if self.last:
@@ -391,29 +458,38 @@ class PipelineExecutor(object):
         tr._last_micro_batch = n_back == self.M
         y = outputs.pop(ins.mb)
         if timing and self.last:                   # split the last stage's backward into host-issue and device time
-          torch.cuda.synchronize(self.device)
+          torch.cuda.current_stream().synchronize()    # (never a device-wide sync here: a posted NCCL receive would never drain)
           _tb0 = _time.perf_counter()
         with phase_scope(ModelPhase.BACKWARD):
-          if self.last:
+          if use_graphs:
+            st = self.graphed[ins.mb % len(self.graphed)]
+            if self.last:
+              gin = st.backward()
+            else:
+              g, req = recv_b.pop(ins.mb)
+              req.wait()
+              gin = st.backward(g)
+            grads_in[ins.mb] = gin
+          elif self.last:
             y.backward()
-            if timing:
-              _tb1 = _time.perf_counter()
-              torch.cuda.synchronize(self.device)
-              _tb2 = _time.perf_counter()
-              host_t["B_issue"] = host_t.get("B_issue", 0.0) + (_tb1 - _tb0)
-              host_t["B_device_after_issue"] = host_t.get("B_device_after_issue", 0.0) + (_tb2 - _tb1)
           else:
             g, req = recv_b.pop(ins.mb)
             req.wait()
             torch.autograd.backward(y, grad_tensors=g)
+        if timing and self.last:
+          _tb1 = _time.perf_counter()
+          torch.cuda.current_stream().synchronize()
+          _tb2 = _time.perf_counter()
+          host_t["B_issue"] = host_t.get("B_issue", 0.0) + (_tb1 - _tb0)
+          host_t["B_device_after_issue"] = host_t.get("B_device_after_issue", 0.0) + (_tb2 - _tb1)
         tr._first_micro_batch = False
       elif ins.op == S.SEND_B:
         x = inputs.pop(ins.mb)
-        sends.append(self.p2p.send_bwd(x.grad.clone() if use_graphs else x.grad.contiguous()))
+        sends.append(self.p2p.send_bwd(grads_in.pop(ins.mb).clone() if use_graphs else x.grad.contiguous()))
       # REDUCE / APPLY are executed by the trainer after the program
     if timing:
       t_issue = _time.perf_counter()
-      torch.cuda.synchronize(self.device)
+      torch.cuda.current_stream().synchronize()
       t_done = _time.perf_counter()
       self._timing_rows = getattr(self, "_timing_rows", 0) + 1
       if self._timing_rows in (3, 5):

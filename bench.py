@@ -42,6 +42,7 @@ def parse():
   ap.add_argument("--model", default="", help="gpt2: tiny|small|medium|large|xl (default xl); bert: tiny|base|large (default large)")
   ap.add_argument("--batch", type=int, default=0, help="sequences (images) per GPU per step (per micro-batch for pipelines)")
   ap.add_argument("--seq", type=int, default=0)
+  ap.add_argument("--layers", type=int, default=0, help="override the number of transformer layers (diagnostics)")
   ap.add_argument("--parallelism", default="auto", help="auto | dp | pp<S> (S-stage pipeline x DP) | tp<N> (bert: split(N))")
   ap.add_argument("--micro-batches", type=int, default=1)
   ap.add_argument("--zero", default="")
@@ -125,7 +126,8 @@ class GPT2Workload(Workload):
                        "the tensor-parallel config of BASELINE.json is --workload bert --model large --parallelism tp8")
     M = args.micro_batches if args.micro_batches > 1 else (8 if stages > 1 else 1)
     batch = args.batch or (8 if stages == 1 else 2)            # pipeline: micro-batch of 2 x 8 micro-batches = 16 per replica
-    cfg = GPT2Config.named(name, num_pipeline_stages=stages, tie_embeddings=(stages == 1), n_positions=max(1024, seq))
+    extra = {"n_layer": args.layers} if args.layers else {}
+    cfg = GPT2Config.named(name, num_pipeline_stages=stages, tie_embeddings=(stages == 1), n_positions=max(1024, seq), **extra)
     self.cfg, self.seq, self.stages, self.M = cfg, seq, stages, M
     torch.manual_seed(1234)
     pure_library = args.impl == "baseline" and stages == 1 and not args.zero and not args.offload
@@ -355,7 +357,7 @@ def main():
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
       run(2, False)
       torch.cuda.synchronize()
-    if rank == 0:
+    if rank == int(os.environ.get("EPL_BENCH_PROFILE_RANK", "0")):
       from easyparallellibrary_b200.profiler.timeline import kernel_table
       text, _ = kernel_table(prof.events())
       with open(args.profile, "w") as f:

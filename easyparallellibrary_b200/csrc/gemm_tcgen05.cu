@@ -832,6 +832,17 @@ EPL_DEVICE int ring_next(const TileRing& r, uint32_t& it, bool whole_warp, int l
   return t;
 }
 
+// Tile order of the 2-CTA kernel: all full-width tiles first (grouped for L2 reuse), the cheap ragged last-column tiles at the
+// very end — with the atomic-counter scheduler this is longest-processing-time-first: the last round of a launch is filled with
+// quarter-cost tiles instead of ending on a full one (N = 1600: 192 full + 32 ragged tiles on 74 CTA pairs).
+EPL_DEVICE void tile_coords2(int tile, int m_blocks, int n_blocks, bool ragged, int& mb, int& nb) {
+  const int n_full = ragged ? n_blocks - 1 : n_blocks;
+  const int full_tiles = m_blocks * n_full;
+  if (tile < full_tiles) { tile_coords(tile, m_blocks, n_full, mb, nb); return; }
+  mb = tile - full_tiles;
+  nb = n_full;
+}
+
 // width of the MMA for the n-block at column n0: the ragged last column tile multiplies only the columns that exist
 // (rounded up to 32 so that each CTA of the pair holds a multiple of 16) instead of a full BN-wide tile
 EPL_DEVICE int tile_n_eff(int N, int n0, int BN) { return min(BN, (N - n0 + 31) & ~31); }
@@ -853,7 +864,7 @@ EPL_DEVICE void gemm2_epilogue(const GemmParams& p, uint32_t tmem_base, uint64_t
     const int tile = ring_next(ring, it, true, lane);
     if (tile >= num_tiles) break;
     int mb, nb;
-    tile_coords(tile, m_blocks, n_blocks, mb, nb);
+    tile_coords2(tile, m_blocks, n_blocks, (p.N % BN) != 0 && n_blocks > 1, mb, nb);
     const int row = mb * BM2 + cta * BLOCK_M + quarter * 32 + lane;
     const int n0 = nb * BN + half * half_cols;                 // this warp's columns
     const bool row_ok = row < p.M;
@@ -984,7 +995,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           if (tile >= num_tiles) break;
         }
         int mb, nb;
-        tile_coords(tile, m_blocks, n_blocks, mb, nb);
+        tile_coords2(tile, m_blocks, n_blocks, (p.N % BN) != 0 && n_blocks > 1, mb, nb);
         const int n_eff = tile_n_eff(p.N, nb * BN, BN);
         const int m0 = mb * BM2 + (int)cta * BLOCK_M, n0 = nb * BN + (int)cta * (n_eff / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -1021,7 +1032,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int tile = ring_next(ring, it, false, 0);
         if (tile >= num_tiles) break;
         int mb, nb;
-        tile_coords(tile, m_blocks, n_blocks, mb, nb);
+        tile_coords2(tile, m_blocks, n_blocks, (p.N % BN) != 0 && n_blocks > 1, mb, nb);
         const uint32_t idesc = make_idesc_f16(BM2, tile_n_eff(p.N, nb * BN, BN), p.ab_format, p.a_mn_major, p.b_mn_major);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -1156,6 +1167,13 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
     p2.M = M; p2.N = N; p2.K = K; p2.ldd = ldd; p2.D = D; p2.bias = bias; p2.pre = pre; p2.aux = aux; p2.epilogue = epilogue;
     p2.accumulate = accumulate; p2.out_dtype = out_dtype; p2.a_mn_major = a_mn_major; p2.b_mn_major = b_mn_major; p2.alpha = alpha;
     p2.ab_format = is_fp16 ? 0 : 1; p2.bn2 = bn2; p2.fp8 = 0; p2.scale_a = p2.scale_b = nullptr;
+    if (accumulate && out_dtype == EPL_BF16 && epilogue == EPI_NONE && (ldd & 7) == 0) {
+      // D += result for a bf16 D is "residual add with the residual = D": the old values are prefetched before the accumulator
+      // wait (aux path) instead of being loaded, added and stored chunk by chunk with the load latency exposed in the epilogue.
+      // Weight-gradient GEMMs of micro-batches 2..M (pipelines, gradient accumulation) and of tied weights take this path; with
+      // 2048-token micro-batches the exposed read-modify-write epilogue made the whole backward 2x slower.
+      p2.epilogue = EPI_BIAS_RESIDUAL; p2.bias = nullptr; p2.aux = D; p2.accumulate = 0;
+    }
     return launch_gemm2(ma2, mb2, p2, sms, (cudaStream_t)stream);
   }
   const int bn = pick_bn(N, b_mn_major, two_cta_forced ? 0 : force_bn);

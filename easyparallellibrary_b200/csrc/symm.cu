@@ -731,3 +731,121 @@ extern "C" int epl_nvls_allreduce(void* mc_ptr, void* const* flag_ptrs, void* lo
   if (epoch == 0) epl::a2a_bump_epoch_kernel<<<1, 1, 0, st>>>((uint32_t*)local_sync + 3);
   return EPL_CHECK_LAUNCH();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 over NVLS: the reduce-scatter is ONE multimem.ld_reduce per 16 bytes of this rank's shard (the NVSwitch adds the W
+// replicas of the gradient bucket in fp32 and returns bf16: only 1/W of the bucket enters the GPU instead of (W-1)/W), the
+// all-gather is ONE multimem.st per 16 bytes (the switch replicates the new weights into every rank's parameter bucket).
+// Per direction and GPU the phase moves (1 + 1/W) x bucket bytes instead of 2 x (W-1)/W x bucket bytes of the peer-pointer
+// kernel (W = 8: 3.5 vs 5.45 GB for GPT-2-XL).  Four vectors per thread are requested before the first is consumed.
+// ---------------------------------------------------------------------------------------------------------
+namespace epl {
+struct FusedNvlsArgs {
+  const void* mc_grads;     // multicast address of this bucket's gradients (element 0 of the bucket)
+  void* mc_params;          // multicast address of this bucket's parameters
+  PeerTable flags;
+  uint32_t* local_sync;
+  float* master; float* m; float* v; const float* mask;
+  int64_t shard_start, shard_n;
+  int rank, world;
+  uint32_t epoch;
+  float beta1, beta2, eps, weight_decay;
+};
+
+template <bool kHasMask>
+__global__ void __launch_bounds__(256) fused_nvls_adam_kernel(const FusedNvlsArgs a, const FusedDpDyn* __restrict__ dyn) {
+  FusedDpArgs b;                                                  // reuse the flag-barrier helpers of the peer-pointer kernel
+  b.flags = a.flags; b.local_sync = a.local_sync; b.rank = a.rank; b.world = a.world;
+  b.epoch = a.epoch ? a.epoch : *reinterpret_cast<volatile uint32_t*>(a.local_sync + 2) + 1u;
+  barrier_start(b);
+  const float lr = dyn->lr, inv_c1 = dyn->inv_c1, inv_c2 = dyn->inv_c2, gscale = dyn->grad_scale;
+  const int64_t nvec = a.shard_n >> 3;
+  const int4* gsrc = reinterpret_cast<const int4*>(reinterpret_cast<const __nv_bfloat16*>(a.mc_grads) + a.shard_start);
+  int4* pdst = reinterpret_cast<int4*>(reinterpret_cast<__nv_bfloat16*>(a.mc_params) + a.shard_start);
+  constexpr int kU = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kU) {
+    uint32_t r[kU][4];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t i = i0 + (int64_t)u * stride;
+      if (i < nvec)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[u][0]), "=r"(r[u][1]), "=r"(r[u][2]), "=r"(r[u][3]) : "l"(gsrc + i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t i = i0 + (int64_t)u * stride;
+      if (i >= nvec) continue;
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(r[u][j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
+      float4 p0 = reinterpret_cast<const float4*>(a.master)[2 * i], p1 = reinterpret_cast<const float4*>(a.master)[2 * i + 1];
+      float4 m0 = reinterpret_cast<const float4*>(a.m)[2 * i], m1 = reinterpret_cast<const float4*>(a.m)[2 * i + 1];
+      float4 v0 = reinterpret_cast<const float4*>(a.v)[2 * i], v1 = reinterpret_cast<const float4*>(a.v)[2 * i + 1];
+      float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float kk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if constexpr (kHasMask) {
+        float4 k0 = reinterpret_cast<const float4*>(a.mask)[2 * i], k1 = reinterpret_cast<const float4*>(a.mask)[2 * i + 1];
+        kk[0] = k0.x; kk[1] = k0.y; kk[2] = k0.z; kk[3] = k0.w; kk[4] = k1.x; kk[5] = k1.y; kk[6] = k1.z; kk[7] = k1.w;
+      }
+      uint32_t packed[4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gr = g[j] * gscale;
+        mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * gr;
+        vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * gr * gr;
+        pp[j] -= lr * ((mm[j] * inv_c1) / (sqrtf(vv[j] * inv_c2) + a.eps) + a.weight_decay * kk[j] * pp[j]);
+      }
+      reinterpret_cast<float4*>(a.master)[2 * i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      reinterpret_cast<float4*>(a.master)[2 * i + 1] = make_float4(pp[4], pp[5], pp[6], pp[7]);
+      reinterpret_cast<float4*>(a.m)[2 * i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(a.m)[2 * i + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
+      reinterpret_cast<float4*>(a.v)[2 * i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      reinterpret_cast<float4*>(a.v)[2 * i + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) packed[j] = pack_bf16x2(pp[2 * j], pp[2 * j + 1]);
+      asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+                   :: "l"(pdst + i), "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
+    }
+  }
+  // end barrier (self-resetting arrival counter, device-side epoch), as in the v2 kernel
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    is_last = (atomicAdd(a.local_sync + 1, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if ((int)threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(a.flags.ptr[threadIdx.x]) + kMaxPeers + a.rank, b.epoch);
+      while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.flags.ptr[a.rank]) + kMaxPeers + threadIdx.x) < b.epoch) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { a.local_sync[1] = 0u; a.local_sync[2] = b.epoch; __threadfence(); }
+  }
+}
+}  // namespace epl
+
+extern "C" int epl_fused_nvls_adam(const void* mc_grads, void* mc_params, void* const* flag_ptrs, void* local_sync, void* master, void* m,
+                                   void* v, const void* mask, int64_t shard_start, int64_t shard_n, int rank, int world, unsigned epoch,
+                                   const void* dyn, float beta1, float beta2, float eps, float weight_decay, int blocks, void* stream) {
+  using namespace epl;
+  if (world > kMaxPeers || (shard_n & 7) || (shard_start & 7)) return -20;
+  FusedNvlsArgs a;
+  a.mc_grads = mc_grads; a.mc_params = mc_params;
+  for (int i = 0; i < kMaxPeers; ++i) a.flags.ptr[i] = i < world ? flag_ptrs[i] : nullptr;
+  a.local_sync = (uint32_t*)local_sync; a.master = (float*)master; a.m = (float*)m; a.v = (float*)v; a.mask = (const float*)mask;
+  a.shard_start = shard_start; a.shard_n = shard_n; a.rank = rank; a.world = world; a.epoch = epoch;
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  if (blocks <= 0) blocks = kNumSMs * 2;
+  blocks = std::min(blocks, kNumSMs * 4);        // all CTAs must become resident eventually; none waits on another except at the start flag
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mask) fused_nvls_adam_kernel<true><<<blocks, 256, 0, st>>>(a, (const FusedDpDyn*)dyn);
+  else fused_nvls_adam_kernel<false><<<blocks, 256, 0, st>>>(a, (const FusedDpDyn*)dyn);
+  return EPL_CHECK_LAUNCH();
+}

@@ -171,7 +171,17 @@ class Graph(object):
       return None
     if module in self._module_tg:
       return self._taskgraphs[self._module_tg[module]]
-    tg = self.current_taskgraph()
+    # a module is registered with its parent AFTER it was built (``self.h = nn.ModuleList(blocks)`` runs when the last
+    # scope is already open): it belongs where its own parameters were created, not where it was attached
+    tg = None
+    if hasattr(module, "parameters"):
+      for p in module.parameters():
+        idx = self._param_tg.get(p)
+        if idx is not None:
+          tg = self._taskgraphs[idx]
+          break
+    if tg is None:
+      tg = self.current_taskgraph()
     self._module_tg[module] = tg.index
     tg.add_module(module)
     return tg

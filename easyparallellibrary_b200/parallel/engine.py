@@ -336,7 +336,20 @@ class Trainer(object):
       state["n"] += 1
       if dtype not in (torch.bfloat16, torch.float16):
         return torch.zeros(numel, dtype=dtype, device=device)
-      buf = SymmetricBuffer(numel * 2, comm.ranks, device, group=getattr(comm.primary, "group", None))
+      pg = getattr(comm.primary, "group", None)
+      buf = None
+      import os as _os
+      if _os.environ.get("EPL_K1", "v2") == "nvls" and pg is not None:
+        # NVLS: allocate the bucket through the VMM + multicast path (runtime/nvls.py); the peer pointers of the same allocation
+        # keep the v2 kernel usable when the platform has no multicast
+        try:
+          from easyparallellibrary_b200.runtime.nvls import MulticastBuffer
+          buf = MulticastBuffer(numel * 2, device, pg)
+        except Exception as e:      # pragma: no cover - platform dependent
+          get_logger().warning("NVLS bucket allocation failed (%s); using cudaIpc symmetric memory", e)
+          buf = None
+      if buf is None:
+        buf = SymmetricBuffer(numel * 2, comm.ranks, device, group=pg)
       self._symm_buffers[(self._cur_stage, kind, dtype)] = buf
       return buf.tensor(dtype, numel)
     return alloc

@@ -49,9 +49,9 @@ class FusedDataParallel(object):
     self.epochs: Dict[Tuple[int, int], int] = {}      # v1 kernel only (v2 keeps its epoch on the device)
     self.side = torch.cuda.Stream(device=trainer.device, priority=-1)
     self.blocks = 148                                 # after backward: the whole GPU
-    self.kernel = os.environ.get("EPL_K1", "v2")      # "v1": the register-path kernel of round 1 (A/B measurements)
+    self.kernel = os.environ.get("EPL_K1", "v2")      # "v1": register-path kernel of round 1; "nvls": multimem.ld_reduce / multimem.st
     self.overlap_blocks = int(os.environ.get("EPL_FUSED_OVERLAP_BLOCKS", "8"))
-    self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "1") != "0" and self.kernel == "v2"
+    self.overlap = os.environ.get("EPL_FUSED_OVERLAP", "1") != "0" and self.kernel in ("v2", "nvls")
     # Each rank's AdamW shard is 1/W of the model, so the bucket kernels' work per rank shrinks with W while their cost to the
     # backward pass (8 SMs taken from every kernel that runs meanwhile + L2 traffic) does not.  Measured, GPT-2-XL, step ms
     # overlapped vs after backward: W=2 149.9 vs 117.5 (eager), W=4 122.6 vs 120.7 (CUDA graph; exposed 5.1 vs 10.5 ms but
@@ -153,6 +153,15 @@ class FusedDataParallel(object):
           opt.master.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), _lib.ptr(opt.decay_mask), lo, hi - lo, comm.rank,
           comm.size, self.epochs[key], _lib.dtype_code(b.dtype), d[0], h.beta1, h.beta2, h.eps, h.weight_decay, d[3],
           d[1], d[2], self.blocks, _lib.stream())
+    elif self.kernel == "nvls" and getattr(gbuf, "multicast_ptr", 0) and b.dtype == torch.bfloat16:
+      if not hasattr(self.lib, "_k1nvls_ready"):
+        self.lib.epl_fused_nvls_adam.argtypes = ([ctypes.c_void_p] * 8 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
+                                                  ctypes.c_void_p] + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_void_p])
+        self.lib._k1nvls_ready = True
+      rc = self.lib.epl_fused_nvls_adam(
+          gbuf.multicast_ptr + b.start * es, pbuf.multicast_ptr + b.start * es, self.pads[s].slot_table(bi), sync.data_ptr(),
+          opt.master.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(), _lib.ptr(opt.decay_mask), lo, hi - lo, comm.rank, comm.size, 0,
+          self.dyn[s].data_ptr(), h.beta1, h.beta2, h.eps, h.weight_decay, (blocks * 4) if blocks else 0, _lib.stream())
     else:
       rc = self.lib.epl_fused_rs_adam_ag_v2(
           gbuf.peer_table(b.start * es), pbuf.peer_table(b.start * es), self.pads[s].slot_table(bi), sync.data_ptr(),

@@ -35,6 +35,7 @@ class MulticastBuffer(object):
     except Exception:          # newer torch enables groups lazily
       pass
     self.storage = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
+    self.storage.zero_()
     self.handle = symm_mem.rendezvous(self.storage, self.group)
     self.rank, self.world = self.handle.rank, self.handle.world_size
     self.multicast_ptr = int(self.handle.multicast_ptr or 0)
@@ -49,8 +50,31 @@ class MulticastBuffer(object):
       lib._nvls_ready = True
     self.lib = lib
 
-  def tensor(self, dtype: torch.dtype, numel: int) -> torch.Tensor:
-    return self.storage[:numel * torch.empty(0, dtype=dtype).element_size()].view(dtype)
+  def tensor(self, dtype: torch.dtype, numel: int, byte_offset: int = 0) -> torch.Tensor:
+    return self.storage[byte_offset:byte_offset + numel * torch.empty(0, dtype=dtype).element_size()].view(dtype)
+
+  # -- drop-in for runtime.symmetric.SymmetricBuffer (the peer-pointer kernels work on the same allocation) ------------------
+  @property
+  def peer_ptrs(self):
+    return [int(p) for p in self.handle.buffer_ptrs]
+
+  @property
+  def local_ptr(self) -> int:
+    return int(self.handle.buffer_ptrs[self.rank])
+
+  def peer_table(self, byte_offset: int = 0):
+    tables = self.__dict__.setdefault("_tables", {})
+    arr = tables.get(byte_offset)
+    if arr is None:
+      arr = (ctypes.c_void_p * 8)()
+      for r, p in enumerate(self.handle.buffer_ptrs):
+        arr[r] = int(p) + byte_offset
+      if len(tables) < 256:
+        tables[byte_offset] = arr
+    return arr
+
+  def close(self) -> None:
+    self.storage = None
 
   def all_reduce_(self, dtype: torch.dtype, numel: int, blocks: int = 32) -> torch.Tensor:
     """In-place sum over the ranks of the first ``numel`` elements (bf16 or fp32; byte count a multiple of 16)."""

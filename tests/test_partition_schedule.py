@@ -127,3 +127,24 @@ def test_receives_are_prefetched():
   # RECV_F(0) and RECV_F(1) are both posted before F(0) runs
   posted = [(i.op, i.mb) for i in last[:first_f]]
   assert (schedule.RECV_F, 0) in posted and (schedule.RECV_F, 1) in posted
+
+
+@pytest.mark.parametrize("family", ["gpt2", "bert"])
+def test_scoped_models_split_their_blocks_evenly(family):
+  """Blocks built between two ``set_default_strategy`` calls belong to the stage that was open when they were BUILT, not to
+  the one open when the ``ModuleList`` holding them was attached (that put every block on the last stage)."""
+  import easyparallellibrary_b200 as epl
+  epl.init(epl.Config({"pipeline.num_micro_batch": 4}))
+  if family == "gpt2":
+    from easyparallellibrary_b200.models.gpt2 import GPT2, GPT2Config, lm_loss
+    model = GPT2(GPT2Config.named("small", num_pipeline_stages=2, tie_embeddings=False))
+    tr = epl.Trainer(model, "adamw", lr=1e-4, loss_fn=lm_loss).build()
+  else:
+    from easyparallellibrary_b200.models.bert import Bert, BertConfig, squad_loss
+    model = Bert(BertConfig.named("base", num_pipeline_stages=2))
+    tr = epl.Trainer(model, "adamw", lr=1e-4, loss_fn=squad_loss).build()
+  layers = model.epl_sequential()
+  assign = tr._assign_layers(layers, epl.Graph.get())
+  n_blocks = len(layers) - 2
+  assert assign.count(0) == 1 + n_blocks // 2 and assign.count(1) == 1 + n_blocks - n_blocks // 2, assign
+  epl.shutdown()

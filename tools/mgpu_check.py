@@ -116,6 +116,26 @@ def train(dev, world, rank, fused, steps=6, model_name="tiny", batch=4, seq=128,
   return tr, losses, flat.clone()
 
 
+def check_fused_nvls(dev, world, rank):
+  """K1 over NVLS (multimem.ld_reduce / multimem.st on multicast-mapped buckets) vs the NCCL path, then its step time."""
+  os.environ["EPL_K1"] = "nvls"
+  try:
+    tr_b, loss_b, p_b = train(dev, world, rank, fused=False, lr=1e-2, eps=1.0)
+    tr_f, loss_f, p_f = train(dev, world, rank, fused=True, lr=1e-2, eps=1.0)
+    assert tr_f.fused is not None and tr_f.fused.kernel == "nvls"
+    bufs = [b for b in tr_f._symm_buffers.values()]
+    nv = all(getattr(b, "multicast_ptr", 0) for b in bufs)
+    diff = (p_b - p_f).abs().max().item()
+    gathered = [torch.zeros_like(p_f) for _ in range(world)]
+    dist.all_gather(gathered, p_f)
+    same = max((gathered[0] - g).abs().max().item() for g in gathered)
+    log("K1 over NVLS (multicast buckets: %s) vs NCCL path (eps=1): max |dparam| = %.3e, replica divergence %.1e, losses %s vs %s" % (
+        nv, diff, same, loss_f[-2:], loss_b[-2:]))
+    assert same == 0.0 and diff < 8e-3 and abs(loss_f[-1] - loss_b[-1]) < 0.03
+  finally:
+    os.environ["EPL_K1"] = "v2"
+
+
 def check_fused(dev, world, rank):
   tr_b, loss_b, p_b = train(dev, world, rank, fused=False)
   assert tr_b.fused is None
@@ -524,7 +544,7 @@ def main():
   torch.cuda.set_device(dev)
   what = sys.argv[1:] or ["native", "symm", "fused"]
   table = [("native", check_native), ("symm", check_symm), ("k1", check_k1), ("k1bench", bench_k1), ("fused", check_fused),
-           ("clip", check_clip), ("tp", check_tp), ("tptrain", check_tp_train), ("moe", check_moe), ("zero3", check_zero3), ("nvls", check_nvls)]
+           ("clip", check_clip), ("tp", check_tp), ("tptrain", check_tp_train), ("moe", check_moe), ("zero3", check_zero3), ("nvls", check_nvls), ("k1nvls", check_fused_nvls)]
   if "all" in what:
     what = [n for n, _ in table if n != "k1bench"]
   for name, fn in table:

@@ -125,7 +125,7 @@ class GPT2Workload(Workload):
       raise SystemExit("GPT-2-XL has 25 attention heads: no tensor-parallel degree in {2,4,8} divides them; "
                        "the tensor-parallel config of BASELINE.json is --workload bert --model large --parallelism tp8")
     M = args.micro_batches if args.micro_batches > 1 else (8 if stages > 1 else 1)
-    batch = args.batch or (8 if stages == 1 else 2)            # pipeline: micro-batch of 2 x 8 micro-batches = 16 per replica
+    batch = args.batch or 8                                    # pipeline: 8 micro-batches of 8 sequences = 64 per replica
     extra = {"n_layer": args.layers} if args.layers else {}
     cfg = GPT2Config.named(name, num_pipeline_stages=stages, tie_embeddings=(stages == 1), n_positions=max(1024, seq), **extra)
     self.cfg, self.seq, self.stages, self.M = cfg, seq, stages, M

@@ -634,9 +634,10 @@ static int make_map_3d_f32(CUtensorMap* map, const void* ptr, uint64_t B, uint64
   cuuint64_t strides[2] = {cols * 4, S * cols * 4};
   cuuint32_t box[3] = {32, kTile, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r;
+  EPL_ENCODE_RETRY(r, ptr, enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
@@ -648,9 +649,10 @@ static int make_map_3d(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t S
   cuuint64_t strides[2] = {cols * 2, S * cols * 2};
   cuuint32_t box[3] = {kD, kTile, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r;
+  EPL_ENCODE_RETRY(r, ptr, enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 

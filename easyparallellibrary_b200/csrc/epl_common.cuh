@@ -19,6 +19,23 @@ enum EplDtype : int { EPL_F32 = 0, EPL_BF16 = 1, EPL_F16 = 2 };
 
 #define EPL_CHECK_LAUNCH() (int)cudaGetLastError()
 
+// Autograd's per-device worker threads bind their CUDA context lazily: a thread whose first CUDA call is a DRIVER call of ours
+// (cuTensorMapEncodeTiled) has no current context and gets CUDA_ERROR_INVALID_CONTEXT (seen on B200: stage 0 of a pipeline,
+// whose backward starts with a GEMM).  Bind the primary context of the device that owns `ptr` and evaluate the call again.
+static inline void epl_bind_context_for(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) cudaSetDevice(a.device);
+  cudaFree(0);
+}
+#define EPL_ENCODE_RETRY(r, ptr, call)                 \
+  do {                                                 \
+    r = (call);                                        \
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {             \
+      epl_bind_context_for(ptr);                       \
+      r = (call);                                      \
+    }                                                  \
+  } while (0)
+
 namespace epl {
 
 constexpr int kNumSMs = 148;

@@ -595,9 +595,13 @@ static int make_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r;
+  EPL_ENCODE_RETRY(r, ptr, enc(map, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+  if (r != CUDA_SUCCESS)
+    fprintf(stderr, "[epl] cuTensorMapEncodeTiled failed (CUresult %d): ptr %p rows %llu cols %llu ld %llu box %u x %u\n", (int)r, ptr,
+            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
@@ -1170,8 +1174,7 @@ extern "C" int epl_gemm(const void* A, const void* B, void* D, int M, int N, int
     if (accumulate && out_dtype == EPL_BF16 && epilogue == EPI_NONE && (ldd & 7) == 0) {
       // D += result for a bf16 D is "residual add with the residual = D": the old values are prefetched before the accumulator
       // wait (aux path) instead of being loaded, added and stored chunk by chunk with the load latency exposed in the epilogue.
-      // Weight-gradient GEMMs of micro-batches 2..M (pipelines, gradient accumulation) and of tied weights take this path; with
-      // 2048-token micro-batches the exposed read-modify-write epilogue made the whole backward 2x slower.
+      // Weight-gradient GEMMs of micro-batches 2..M (pipelines, gradient accumulation) and of tied weights take this path.
       p2.epilogue = EPI_BIAS_RESIDUAL; p2.bias = nullptr; p2.aux = D; p2.accumulate = 0;
     }
     return launch_gemm2(ma2, mb2, p2, sms, (cudaStream_t)stream);
@@ -1205,8 +1208,9 @@ static int make_map_2d_u8(CUtensorMap* map, const void* ptr, uint64_t rows, uint
   cuuint64_t strides[1] = {ld};
   cuuint32_t box[2] = {128, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  EPL_ENCODE_RETRY(r, ptr, enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 

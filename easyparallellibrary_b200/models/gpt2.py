@@ -147,14 +147,20 @@ class GPT2(nn.Module):
     stages = max(cfg.num_pipeline_stages, 1)
     if stages > 1 and cfg.tie_embeddings:
       raise ValueError("tied embeddings cannot be split across pipeline stages; set tie_embeddings=False")
-    per = (cfg.n_layer + stages - 1) // stages
+    # stage boundaries balance FLOPs, not block counts: the vocabulary projection costs as much as V / (12 d) blocks
+    # (2.6 blocks for GPT-2-XL) and sits on the last stage, so that stage gets fewer blocks
+    head_blocks = cfg.vocab_size / (12.0 * cfg.n_embd)
+    target = (cfg.n_layer + head_blocks) / stages
+    starts = {}
+    for k in range(1, stages):
+      starts[min(max(int(round(k * target)), k), cfg.n_layer - (stages - k))] = k
     blocks = []
     if stages > 1:
       epl.set_default_strategy(epl.replicate(1, name="stage_0"))
     self.embed = Embedding(cfg)
     for i in range(cfg.n_layer):
-      if stages > 1 and i > 0 and i % per == 0:
-        epl.set_default_strategy(epl.replicate(1, name="stage_%d" % (i // per)))   # opens the next taskgraph
+      if stages > 1 and i in starts:
+        epl.set_default_strategy(epl.replicate(1, name="stage_%d" % starts[i]))   # opens the next taskgraph
       blocks.append(Block(cfg))
     self.h = nn.ModuleList(blocks)
     self.head = Head(cfg, self.embed.wte.weight if cfg.tie_embeddings else None)

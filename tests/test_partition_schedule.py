@@ -146,5 +146,7 @@ def test_scoped_models_split_their_blocks_evenly(family):
   layers = model.epl_sequential()
   assign = tr._assign_layers(layers, epl.Graph.get())
   n_blocks = len(layers) - 2
-  assert assign.count(0) == 1 + n_blocks // 2 and assign.count(1) == 1 + n_blocks - n_blocks // 2, assign
+  # GPT-2 weighs the vocabulary projection (5.45 blocks' worth for "small") onto the last stage: 9 + 3 blocks; BERT: 6 + 6
+  first = round((n_blocks + 50257 / (12.0 * 768)) / 2) if family == "gpt2" else n_blocks // 2
+  assert assign.count(0) == 1 + first and assign.count(1) == 1 + n_blocks - first, assign
   epl.shutdown()

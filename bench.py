@@ -350,6 +350,19 @@ def main():
       apply_ms[0] = float(t[1].item()) if float(t[1].item()) >= 0 else None
     return float(t[0].item()), loss, clocks, _lib.launches - l0
 
+  # set-up, not warm-up: the trainer runs its first GraphedStep.WARMUP steps eagerly and CAPTURES the CUDA graph of the step in
+  # the next one (a pipeline captures its stage graphs in its first step).  Do that here, so that whatever --warmup says, the W
+  # warm-up steps and the K timed steps all run the steady-state program (with --warmup 3 the capture used to land on the first
+  # timed step: 8-GPU session of round 2, profiles/r2_session_8gpu.md).
+  setup_steps = 0
+  g = getattr(trainer, "_graphed", None) if trainer is not None else None
+  if g is not None and g.enabled:
+    setup_steps = g.WARMUP + 1
+  elif getattr(wl, "stages", 1) > 1:
+    setup_steps = 1
+  if setup_steps:
+    run(setup_steps, False)
+    barrier()
   run(max(args.warmup, 3), False)
   if args.profile:                               # kernel timeline of 2 steps (CUPTI via torch.profiler); never a bench value
     from torch.profiler import profile, ProfilerActivity
@@ -397,6 +410,10 @@ def main():
       cfg["gradient_buckets"] = sum(len(f.buckets) for f in trainer.flats.values())
     cfg.update(wl.meta)
     cfg["cuda_graph"] = bool(graphed)
+    pipe = getattr(trainer, "pipe", None) if trainer is not None else None
+    if pipe is not None and getattr(pipe, "graphed", None):
+      cfg["cuda_graph"] = "per stage: forward and backward of a micro-batch replay from CUDA graphs"
+    cfg["setup_steps_before_warmup"] = setup_steps
     line = {
         "metric": wl.metric, "value": value, "unit": wl.unit + "/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -371,7 +371,9 @@ def check_tp_train(dev, world, rank):
     epl.init(epl.Config({"amp.level": "bf16", "cluster.colocate_split_and_replicate": True}))
     epl.set_default_strategy(epl.replicate(device_count=1))
     torch.manual_seed(0)
-    model = Bert(BertConfig.named("tiny", hidden_size=256, num_attention_heads=4, intermediate_size=1024, tensor_parallel=world))
+    heads = max(4, world)                                                # at least one 64-wide head per tensor-parallel rank
+    model = Bert(BertConfig.named("tiny", hidden_size=64 * heads, num_attention_heads=heads, intermediate_size=256 * heads,
+                                  tensor_parallel=world))
     tr = epl.Trainer(model, "adamw", lr=1e-3, eps=1.0).build()          # eps=1: no sign amplification of rounding differences
     g = torch.Generator().manual_seed(3)                                 # the whole TP group sees the same batch
     losses = []
@@ -547,13 +549,29 @@ def main():
            ("clip", check_clip), ("tp", check_tp), ("tptrain", check_tp_train), ("moe", check_moe), ("zero3", check_zero3), ("nvls", check_nvls), ("k1nvls", check_fused_nvls)]
   if "all" in what:
     what = [n for n, _ in table if n != "k1bench"]
+  failed = []
   for name, fn in table:
     if name in what:
-      fn(dev, world, rank)
-      torch.cuda.synchronize()
-      dist.barrier()
-      log("CHECK %s PASSED (world %d)" % (name, world))
+      try:                                             # a failing check (same exception on every rank) must not hide the later ones
+        fn(dev, world, rank)
+        torch.cuda.synchronize()
+        ok = 1
+      except Exception:
+        import traceback
+        traceback.print_exc()
+        ok = 0
+      t = torch.tensor([ok], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MIN)
+      if int(t.item()):
+        log("CHECK %s PASSED (world %d)" % (name, world))
+      else:
+        failed.append(name)
+        log("CHECK %s FAILED (world %d)" % (name, world))
   dist.barrier()
+  if failed:
+    log("MGPU CHECK FAILED: %s" % ", ".join(failed))
+    dist.destroy_process_group()
+    sys.exit(1)
   log("MGPU CHECK PASSED")
   dist.destroy_process_group()
 

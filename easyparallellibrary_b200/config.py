@@ -53,6 +53,8 @@ _opt("zero", "level", "", "'' | v0 | v1 | v2 | v3.")
 _opt("zero", "fused_gather", False,
      "B200 extension (v3): gather the weight of a layer's first GEMM inside that GEMM instead of before it.")
 _opt("offload", "level", "", "'' | v0 (weights and optimizer state live on the host).")
+_opt("offload", "weights", True,
+     "B200 extension (v0): False keeps the weights on the device and offloads the optimizer state only.")
 _opt("amp", "level", "", "'' | O1 (fp16 + loss scale) | bf16 | fp8 (B200 extension: bf16 weights, e4m3 forward GEMMs).")
 _opt("amp", "debug_log", False, "Log the precision decision for every module.")
 _opt("amp", "loss_scale", "dynamic", "'dynamic' or a fixed number.")

@@ -258,7 +258,9 @@ class Trainer(object):
                                                            and not self.baseline)) and comm.size > 1
       self._sharded[s] = self.sharded
       shard_world = comm.size if self.sharded else 1
-      if zero == "v3" and s < 1000:
+      # offload.level=v0 keeps the WEIGHTS on the host too (reference graph_editor.py:727-751): that is the per-layer
+      # partition / gather-just-in-time engine of ZeRO-3 with its shards in pinned host memory, at any world size (1 included)
+      if (zero == "v3" or (cfg.offload.level == "v0" and cfg.offload.weights)) and s < 1000:
         from easyparallellibrary_b200.parallel.zero3 import Zero3Engine
         root = self.stage_modules[s]
         units = sequential_layers(root) or [c for c in root.children()]

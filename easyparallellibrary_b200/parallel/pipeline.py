@@ -129,15 +129,23 @@ class _StageFn(torch.nn.Module):
   of its own, so ``torch.cuda.make_graphed_callables`` can capture it.  Several instances share the same inner module
   (one per micro-batch that may be in flight: the captured graphs own the saved activations)."""
 
-  def __init__(self, module, loss_fn, factor: float):
+  def __init__(self, module, loss_fn, factor: float, device=None):
     super().__init__()
     self.module, self.loss_fn, self.factor = module, loss_fn, float(factor)
+    # loss scale x 1/M as a DEVICE scalar: a dynamic loss scale changes between steps, and a Python float would be baked into
+    # the captured graph (set_factor refreshes it before a replay)
+    self.factor_t = torch.full((), float(factor), dtype=torch.float32, device=device) if loss_fn is not None else None
+
+  def set_factor(self, factor: float) -> None:
+    if self.factor_t is not None and float(factor) != self.factor:
+      self.factor = float(factor)
+      self.factor_t.fill_(self.factor)
 
   def forward(self, x, *labels):
     y = self.module(x)
     if self.loss_fn is not None:
       y = self.loss_fn(y, *labels)
-      return y * self.factor if self.factor != 1.0 else y
+      return y * self.factor_t.to(y.dtype)
     return y
 
 
@@ -261,7 +269,8 @@ class PipelineExecutor(object):
     if self.last and loss_fn is None:
       self.use_graphs = False
       return
-    fn = _StageFn(self.module, loss_fn, factor if self.last else 1.0)
+    fn = _StageFn(self.module, loss_fn, factor if self.last else 1.0, device=self.device)
+    self.stage_fn = fn
     self.stage_factor = fn.factor
     labels = tuple(t.clone() for t in mb[1:] if isinstance(t, torch.Tensor)) if self.last else ()
     if self.last and len(labels) != len(mb) - 1:
@@ -381,6 +390,9 @@ class PipelineExecutor(object):
       for p in self.module.parameters():
         if hasattr(p, "epl_sink_fresh"):
           p.epl_sink_fresh = False
+      if self.last:                               # the (dynamic) loss scale of THIS step, read by the captured graph from device memory
+        self.stage_fn.set_factor(tr.scaler.loss_scale * ((1.0 / self.M) if (mean and self.M > 1) else 1.0))
+        self.stage_factor = self.stage_fn.factor
     inputs: Dict[int, torch.Tensor] = {}
     outputs: Dict[int, torch.Tensor] = {}
     recv_f: Dict[int, Tuple[torch.Tensor, Any]] = {}

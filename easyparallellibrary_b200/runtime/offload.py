@@ -9,10 +9,10 @@ link (PCIe Gen5, ~55 GB/s) is two orders of magnitude slower than HBM, so the de
   device window on a dedicated copy stream (``cudaMemcpyAsync``), the fused AdamW kernel runs on the
   window, and the results stream back — H2D of chunk *i+1* and D2H of chunk *i-1* overlap the kernel on
   chunk *i*.  Device memory drops by 12 B/param.
-* **parameter offload** (:class:`ParameterOffloader`): module weights live in pinned host memory and are
-  prefetched one module ahead of their use on the copy stream (forward pre-hooks), released after use —
-  the literal "weights on host, read just in time" behaviour of the reference, with the copy hidden
-  behind the previous module's compute.
+* **weight offload**: with ``offload.weights`` (default) the model runs through the per-layer engine of
+  ``parallel/zero3.py`` with its weight shards in pinned host memory: a layer's weights are copied in (and, across
+  ranks, all-gathered) one layer ahead of their use on a copy stream and released after use — the literal "weights on
+  host, read just in time" behaviour of the reference, with the copy hidden behind the previous layer's compute.
 """
 from __future__ import annotations
 
@@ -98,73 +98,3 @@ class OffloadedOptimizer(FlatOptimizer):
         ev.record(cs)
         free[i % 2] = ev
     main.wait_stream(cs)
-
-
-class ParameterOffloader(object):
-  """Keep the weights of ``modules`` in pinned host memory; stream them in one module ahead of use."""
-
-  def __init__(self, modules: List[nn.Module], device: torch.device, prefetch: int = 1):
-    self.modules, self.device, self.prefetch = list(modules), device, prefetch
-    self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
-    self.host: Dict[int, List[torch.Tensor]] = {}
-    self.events: Dict[int, object] = {}
-    for i, m in enumerate(self.modules):
-      hs = []
-      for p in m.parameters(recurse=True):
-        h = p.data.detach().to("cpu")
-        if device.type == "cuda":
-          h = h.pin_memory()
-        hs.append(h)
-        p.data = torch.empty(0, dtype=p.dtype, device=device)
-      self.host[i] = hs
-      m.register_forward_pre_hook(self._make_pre(i))
-      m.register_forward_hook(self._make_post(i))
-    self.resident = set()
-
-  def _fetch(self, i: int) -> None:
-    if i in self.resident or i >= len(self.modules):
-      return
-    m = self.modules[i]
-    ctx = torch.cuda.stream(self.stream) if self.stream is not None else _null()
-    with ctx:
-      for p, h in zip(m.parameters(recurse=True), self.host[i]):
-        p.data = h.to(self.device, non_blocking=True)
-      if self.stream is not None:
-        ev = torch.cuda.Event()
-        ev.record(self.stream)
-        self.events[i] = ev
-    self.resident.add(i)
-
-  def _make_pre(self, i: int):
-    def pre(mod, args):
-      self._fetch(i)
-      for j in range(1, self.prefetch + 1):
-        self._fetch(i + j)
-      if i in self.events:
-        torch.cuda.current_stream().wait_event(self.events.pop(i))
-    return pre
-
-  def _make_post(self, i: int):
-    def post(mod, args, out):
-      if torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters()):
-        return                                  # backward still needs the weights; released by release_all()
-      self.release(i)
-    return post
-
-  def release(self, i: int) -> None:
-    if i in self.resident:
-      for p in self.modules[i].parameters(recurse=True):
-        p.data = torch.empty(0, dtype=p.dtype, device=self.device)
-      self.resident.discard(i)
-
-  def release_all(self, write_back: bool = False) -> None:
-    for i in list(self.resident):
-      if write_back:
-        for p, h in zip(self.modules[i].parameters(recurse=True), self.host[i]):
-          h.copy_(p.data, non_blocking=True)
-      self.release(i)
-
-
-class _null(object):
-  def __enter__(self): return self
-  def __exit__(self, *a): return False

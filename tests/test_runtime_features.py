@@ -49,10 +49,15 @@ def test_gradient_checkpoint_auto_and_collection_match_plain():
 
 def test_offload_and_grouped_apply_match_plain():
   base, _ = _run({})
-  off, tr = _run({"offload.level": "v0"})
+  off, tr = _run({"offload.level": "v0", "offload.weights": False})            # optimizer state only
   assert max(abs(a - b) for a, b in zip(base, off)) < 1e-6
   from easyparallellibrary_b200.runtime.offload import OffloadedOptimizer
-  assert all(isinstance(o, OffloadedOptimizer) for o in tr.optimizers[0])
+  assert all(isinstance(o, OffloadedOptimizer) for o in tr.optimizers[0]) and not tr.zero3
+  off, tr = _run({"offload.level": "v0"})                                       # weights too: the per-layer engine, shards on the host
+  assert max(abs(a - b) for a, b in zip(base, off)) < 1e-6
+  units = tr.zero3[0].units
+  assert units and all(u.offload and isinstance(u.opt, OffloadedOptimizer) for u in units)
+  assert all(p.numel() == 0 for u in units for p in u.params)                   # released between steps
   grp, _ = _run({"optimizer.num_apply_group": 4})
   assert max(abs(a - b) for a, b in zip(base, grp)) < 1e-6
   ga, _ = _run({"pipeline.num_micro_batch": 4})

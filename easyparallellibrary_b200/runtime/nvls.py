@@ -5,7 +5,7 @@ A :class:`MulticastBuffer` is a symmetric allocation that is ADDITIONALLY bound 
 store out to every rank's copy and lets ``multimem.ld_reduce`` return the switch-side sum of all copies.  The VMM /
 multicast plumbing (POSIX file-descriptor hand-off between the processes included) is ``torch.distributed``'s
 symmetric-memory rendezvous — control plane, like the process group itself; the data plane is the in-tree kernel
-``csrc/symm.cu::nvls_allreduce_kernel`` (``multimem.ld_reduce`` + ``multimem.st``, SASS ``LDGMC`` / ``STGMC``).
+``csrc/symm.cu::nvls_allreduce_kernel`` (``multimem.ld_reduce`` + ``multimem.st``, SASS ``LDGMC.E.HPADD`` for the reduce-load; the multicast store is a ``STG.E.128.STRONG.SYS`` on the multicast address).
 
 Availability is a property of the platform (NVSwitch fabric + driver + container permissions): ``MulticastBuffer.supported``
 tells; callers fall back to the peer-pointer path (``runtime/symmetric.py``) when it is False.

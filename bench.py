@@ -404,9 +404,13 @@ def main():
     flops = wl.flops_per_unit * value / world
     cfg = dict(wl.config)
     if trainer is not None and getattr(trainer, "fused", None) is not None:
-      cfg["dp_gradient_path"] = "fused reduce-scatter + AdamW + all-gather kernel (K1 v2), %s" % (
-          "overlapped with backward on %d CTAs, last bucket on the whole GPU" % trainer.fused.overlap_blocks if trainer.fused.overlap
-          else "after backward")
+      dp_size = max(c.size for c in trainer.dp_comms.values())
+      overlapped = (trainer.fused.overlap and dp_size >= trainer.fused.overlap_min_world and not trainer.plan.pipeline
+                    and trainer.max_grad_norm is None)
+      cfg["dp_gradient_path"] = "fused reduce-scatter + AdamW + all-gather kernel (K1 %s), %s" % (
+          trainer.fused.kernel,
+          "overlapped with backward on %d CTAs, last bucket on the whole GPU" % trainer.fused.overlap_blocks if overlapped
+          else "after backward (overlap starts at %d-way data parallelism)" % trainer.fused.overlap_min_world)
       cfg["gradient_buckets"] = sum(len(f.buckets) for f in trainer.flats.values())
     cfg.update(wl.meta)
     cfg["cuda_graph"] = bool(graphed)

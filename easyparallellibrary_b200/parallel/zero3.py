@@ -20,6 +20,11 @@ import torch
 from torch import nn
 
 import os
+import warnings
+
+# the backward PRE-hooks below also sit on the first unit, whose inputs (token ids) need no gradient; torch then warns that a
+# full backward hook "is firing when gradients are computed with respect to module outputs" — exactly what is wanted here
+warnings.filterwarnings("ignore", message="Full backward hook is firing when gradients are computed with respect to module outputs")
 
 from easyparallellibrary_b200.parallel.flat import ALIGN_ELEMS
 from easyparallellibrary_b200.runtime.optimizer import FlatOptimizer

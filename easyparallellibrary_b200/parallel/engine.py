@@ -619,9 +619,14 @@ class Trainer(object):
       for s in range(self.plan.num_stages):
         x = self.stage_modules[s](x)
       out = x
-      return self.loss_fn(out, *mb[1:]) if self.loss_fn is not None else _as_loss(out)
+      if self.loss_fn is not None and (len(mb) > 1 or torch.is_grad_enabled()):
+        return self.loss_fn(out, *mb[1:])
+      return out if not torch.is_grad_enabled() else _as_loss(out)       # eval_step(inputs) without labels: the model's output
     if self.loss_fn is not None:
-      return self.loss_fn(self.model(mb[0], **kwargs), *mb[1:])
+      out = self.model(mb[0], **kwargs)
+      if len(mb) == 1 and not torch.is_grad_enabled():
+        return out                                                       # eval_step(inputs) without labels: the model's output
+      return self.loss_fn(out, *mb[1:])
     return _as_loss(self.model(*mb, **kwargs))
 
   # ------------------------------------------------------------------ reduce + apply

@@ -539,7 +539,9 @@ class PipelineExecutor(object):
         self._meta_sent = True
       self.p2p.send_fwd(y.contiguous()).wait()
       return None
-    return self.tr.loss_fn(y, *batch[1:]) if self.tr.loss_fn is not None else y
+    if self.tr.loss_fn is not None and len(batch) > 1:
+      return self.tr.loss_fn(y, *batch[1:])
+    return y                                         # no labels: the last stage returns the model's output (predictions)
 
   def all_reduce_over_stages(self, t: torch.Tensor) -> torch.Tensor:
     dist.all_reduce(t, group=self.replica_group)

@@ -217,6 +217,16 @@ def predict(trainer, examples, feats, batch_size, max_answer_length=30):
             score = float(s_log[s] + e_log[e])
             if score > best.get(f.example_index, (-1e30,))[0]:
               best[f.example_index] = (score, f.token_to_word[s], f.token_to_word[e])
+  import torch.distributed as dist
+  if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    # under pipeline parallelism only the last stage of a replica sees the logits: merge every rank's best spans
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, best)
+    best = {}
+    for part in parts:
+      for k, v in part.items():
+        if v[0] > best.get(k, (-1e30,))[0]:
+          best[k] = v
   em = f1 = 0.0
   for ei, ex in enumerate(examples):
     if ei in best:
@@ -257,6 +267,8 @@ def main():
   ap.add_argument("--zero", default="")
   ap.add_argument("--offload", default="")
   ap.add_argument("--io_slicing", action="store_true")
+  ap.add_argument("--auto_parallel", action="store_true",
+                  help="let the planner cut the layer stack into --num_pipe_stages stages (reference run_squad_auto_pipe.py)")
   args = ap.parse_args()
   rank = int(os.environ.get("RANK", 0))
   if args.model == "tiny":
@@ -265,6 +277,8 @@ def main():
   epl.init(epl.Config({"pipeline.num_micro_batch": args.num_micro_batch, "gradient_checkpoint.type": args.gc,
                        "amp.level": args.amp if torch.cuda.is_available() else "", "zero.level": args.zero,
                        "offload.level": args.offload, "io.slicing": args.io_slicing,
+                       "auto.auto_parallel": args.auto_parallel,
+                       "pipeline.num_stages": args.num_pipe_stages if args.auto_parallel else -1,
                        "cluster.colocate_split_and_replicate": args.tensor_parallel > 1}))
   if args.tensor_parallel > 1:
     epl.set_default_strategy(epl.replicate(device_count=1))
@@ -272,7 +286,8 @@ def main():
   train_file = args.train_file or synthetic_squad(os.path.join(args.output_dir, "train-synthetic.json"), args.synthetic_paragraphs, 0)
   predict_file = args.predict_file or synthetic_squad(os.path.join(args.output_dir, "dev-synthetic.json"), max(args.synthetic_paragraphs // 6, 4), 1)
   train_examples = read_squad_examples(train_file)
-  bcfg = BertConfig.named(args.model, num_pipeline_stages=args.num_pipe_stages, tensor_parallel=args.tensor_parallel,
+  bcfg = BertConfig.named(args.model, num_pipeline_stages=1 if args.auto_parallel else args.num_pipe_stages,
+                          tensor_parallel=args.tensor_parallel,
                           max_position_embeddings=max(512, args.max_seq_length))
   if args.vocab_file:
     tok = WordPieceTokenizer([l.rstrip("\n") for l in open(args.vocab_file)])
@@ -281,7 +296,7 @@ def main():
   assert len(tok.vocab) <= bcfg.vocab_size
 
   model = Bert(bcfg)
-  loss_fn = squad_loss if args.num_pipe_stages > 1 else None
+  loss_fn = squad_loss if (args.num_pipe_stages > 1 or args.auto_parallel) else None
   trainer = epl.Trainer(model, "adamw", lr=args.learning_rate, weight_decay=0.01, loss_fn=loss_fn).build()
   if args.resume and os.path.exists(os.path.join(args.output_dir, "ckpt")):
     step0 = load_checkpoint(trainer, os.path.join(args.output_dir, "ckpt"))

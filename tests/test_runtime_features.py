@@ -273,6 +273,9 @@ def test_launcher_runs_a_two_process_job(tmp_path, amp):
     ("train_moe.py", ["--batch", "2", "--seq", "16", "--steps", "2", "--experts", "4"]),
     ("moe/train_t5_moe.py", ["--size", "tiny", "--batch", "2", "--seq", "32", "--steps", "3", "--experts", "4"]),
     ("resnet/resnet_dp.py", ["--width", "8", "--classes", "32", "--image", "32", "--batch", "4", "--steps", "2", "--gc", "auto"]),
+    ("resnet/resnet_split.py", ["--width", "8", "--classes", "32", "--image", "32", "--batch", "4", "--steps", "2"]),
+    ("bert/run_squad.py", ["--model", "tiny", "--do_train", "--do_predict", "--num_train_steps", "3", "--train_batch_size", "4", "--synthetic_paragraphs", "8",
+                           "--output_dir", "/tmp/epl_squad_pytest_auto", "--auto_parallel", "--num_pipe_stages", "2", "--num_micro_batch", "2"]),
     ("bert/run_squad.py", ["--model", "tiny", "--do_train", "--do_predict", "--num_train_steps", "3", "--train_batch_size", "4",
                            "--synthetic_paragraphs", "8", "--output_dir", "/tmp/epl_squad_pytest"]),
 ])

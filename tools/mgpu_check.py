@@ -548,7 +548,10 @@ def main():
   table = [("native", check_native), ("symm", check_symm), ("k1", check_k1), ("k1bench", bench_k1), ("fused", check_fused),
            ("clip", check_clip), ("tp", check_tp), ("tptrain", check_tp_train), ("moe", check_moe), ("zero3", check_zero3), ("nvls", check_nvls), ("k1nvls", check_fused_nvls)]
   if "all" in what:
-    what = [n for n, _ in table if n != "k1bench"]
+    # the NVLS checks have only been validated at 2 ranks: beyond that they must be asked for by name (a hang inside "all"
+    # would take the asserted checks of tests/test_multigpu.py down with it)
+    skip = {"k1bench"} | ({"nvls", "k1nvls"} if world > 2 and os.environ.get("EPL_CHECK_NVLS", "0") != "1" else set())
+    what = [n for n, _ in table if n not in skip]
   failed = []
   for name, fn in table:
     if name in what:

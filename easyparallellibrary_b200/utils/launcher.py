@@ -38,6 +38,9 @@ def parse(argv=None):
   ap.add_argument("--debug", action="store_true")
   ap.add_argument("--log_dir", default=".")
   ap.add_argument("--backend", default="", help="force 'gloo' to run the plumbing on CPUs")
+  ap.add_argument("--max_restarts", type=int, default=0,
+                  help="relaunch the whole local group this many times after a failed attempt (EPL_RESTART_COUNT tells the script "
+                       "which attempt it is; scripts resume from their last checkpoint, e.g. examples/bert/run_squad.py --resume)")
   ap.add_argument("script")
   ap.add_argument("script_args", nargs=argparse.REMAINDER)
   return ap.parse_args(argv)
@@ -72,11 +75,28 @@ def build_commands(args) -> List[dict]:
 
 
 def main(argv=None) -> int:
+  """Run the job; after a failed attempt tear every process down (by exact PID) and, with ``--max_restarts``, start over with a
+  fresh rendezvous port — the reference's ``run_script`` retry loop (``utils/launcher.py:168-188``) with recovery from the last
+  checkpoint instead of a blind re-run."""
   args = parse(argv)
+  rc = 0
+  for attempt in range(max(args.max_restarts, 0) + 1):
+    rc = _run_once(args, attempt)
+    if rc == 0:
+      break
+    if attempt < args.max_restarts:
+      print("[epl-launch] attempt %d failed with exit code %d; restarting (%d left)" % (attempt, rc, args.max_restarts - attempt),
+            file=sys.stderr, flush=True)
+      time.sleep(1.0)
+  return rc
+
+
+def _run_once(args, attempt: int) -> int:
   os.makedirs(args.log_dir, exist_ok=True)
   procs = []
   for c in build_commands(args):
-    err = open(os.path.join(args.log_dir, "stderr_%d.log" % c["rank"]), "w")
+    c["env"]["EPL_RESTART_COUNT"] = str(attempt)
+    err = open(os.path.join(args.log_dir, "stderr_%d.log" % c["rank"]), "a" if attempt else "w")
     procs.append((c["rank"], subprocess.Popen(c["argv"], env=c["env"], stderr=err if not args.debug else None), err))
   rc = 0
   try:
@@ -86,7 +106,7 @@ def main(argv=None) -> int:
         if r in alive and p.poll() is not None:
           alive.discard(r)
           if p.returncode != 0:
-            rc = p.returncode
+            rc = rc or p.returncode       # report the first failure, not the SIGTERM of the ranks torn down because of it
             for _, q, _ in procs:          # tear down by exact PID
               if q.poll() is None:
                 q.send_signal(signal.SIGTERM)

@@ -3,6 +3,7 @@ checkpoint save/resume, ShardingLoader, IO slicing, profiler hooks, auto stage s
 Tolerances follow the reference's A/B tests (|dloss| < 1e-6 offload / grouped apply, < 1e-5 checkpoint)."""
 import json
 import os
+import time
 
 import pytest
 import torch
@@ -180,6 +181,27 @@ def test_launcher_command_lines():
                          "--machine_rank", "1", "run.sh"])
   cmds = launcher.build_commands(args)
   assert len(cmds) == 16 and cmds[0]["rank"] == 16 and cmds[0]["env"]["MASTER_ADDR"] == "10.0.0.1" and cmds[0]["argv"][0] == "bash"
+
+
+def test_launcher_restarts_a_failed_job(tmp_path):
+  """``epl-launch --max_restarts``: a job whose rank 1 dies in the first attempt is torn down and relaunched; the script sees
+  which attempt it is (EPL_RESTART_COUNT) and, like a real job resuming from a checkpoint, succeeds the second time."""
+  from easyparallellibrary_b200.utils import launcher
+  script = tmp_path / "job.py"
+  script.write_text(
+      "import os, sys, time\n"
+      "rank, attempt = int(os.environ['RANK']), int(os.environ['EPL_RESTART_COUNT'])\n"
+      "open(os.path.join(%r, 'ran_%%d_%%d' %% (attempt, rank)), 'w').close()\n"
+      "if attempt == 0 and rank == 1:\n"
+      "  sys.exit(3)\n"
+      "if attempt == 0:\n"
+      "  time.sleep(30)          # a healthy rank of the failed attempt must be terminated, not waited for\n" % str(tmp_path))
+  t0 = time.time()
+  assert launcher.main(["--num_workers", "1", "--gpu_per_worker", "2", "--backend", "gloo", "--log_dir", str(tmp_path), str(script)]) == 3
+  assert launcher.main(["--num_workers", "1", "--gpu_per_worker", "2", "--backend", "gloo", "--log_dir", str(tmp_path), "--max_restarts", "1",
+                        str(script)]) == 0
+  assert time.time() - t0 < 25
+  assert all((tmp_path / ("ran_%d_%d" % (a, r))).exists() for a in (0, 1) for r in (0, 1))
 
 
 def test_models_build_and_step_on_cpu():

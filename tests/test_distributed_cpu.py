@@ -451,3 +451,34 @@ def test_four_stage_pipeline_matches_single_process(policy):
   for r in res:
     for a, b in zip(r[0], base[0]):
       assert abs(a - b) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- train / evaluate loops
+def _loop_pipe_worker(rank, world, stages):
+  """``epl.train_and_evaluate`` under a pipeline: every stage takes part in every evaluation forward, only the last stage gets a
+  result (loss with labels, model output without), and the evaluation barrier keeps the ranks together."""
+  import easyparallellibrary_b200 as epl
+  epl.init(epl.Config({"pipeline.num_micro_batch": 2}))
+  torch.manual_seed(0)
+  per = len(_LAYER_FACTORIES) // stages
+  mods = []
+  for s in range(stages):
+    with epl.replicate(device_count=1, name="stage%d" % s):
+      mods.append(nn.Sequential(*[f() for f in _LAYER_FACTORIES[s * per:(s + 1) * per]]))
+  tr = epl.Trainer(nn.Sequential(*mods), "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2).build()
+  g = torch.Generator().manual_seed(7)
+  data = [(torch.randn(8, 10, generator=g), torch.randn(8, 1, generator=g)) for _ in range(3)]
+  hist = epl.train_and_evaluate(tr, data, data[:2], max_steps=4, eval_every=2)
+  outs = epl.evaluate(tr, [x for x, _ in data[:2]], metric_fn=lambda out, batch: {"rows": out.shape[0]})
+  return [(h["global_step"], h["batches"], h.get("loss")) for h in hist], outs, tr.plan.pipeline
+
+
+def test_train_and_evaluate_under_a_pipeline():
+  base = run_distributed(_loop_pipe_worker, 1, args=(2,))[0]
+  res = run_distributed(_loop_pipe_worker, 2, args=(2,))
+  assert res[0][2] and res[1][2] and not base[2]
+  # rank 0 holds stage 0: it runs every evaluation forward but sees no result; rank 1 (last stage) reports what one process reports
+  assert [h[:2] for h in res[0][0]] == [(2, 0), (4, 0)] and res[0][1]["batches"] == 0
+  assert [h[:2] for h in res[1][0]] == [(2, 2), (4, 2)] and res[1][1] == {"rows": 8.0, "batches": 2}
+  for a, b in zip(res[1][0], base[0]):
+    assert abs(a[2] - b[2]) < 1e-5

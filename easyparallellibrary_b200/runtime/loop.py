@@ -76,11 +76,14 @@ def train(trainer, data: Iterable, max_steps: int, checkpoint_dir: Optional[str]
 
 @torch.no_grad()
 def evaluate(trainer, data: Iterable, metric_fn: Optional[Callable[[Any, Tuple[Any, ...]], Dict[str, float]]] = None,
-             max_batches: int = 0) -> Dict[str, float]:
+             max_batches: int = 0, reduce: bool = True) -> Dict[str, float]:
   """Forward-only pass over ``data``.  With ``metric_fn(output, batch) -> {name: value}`` the values are averaged over batches
   (``output`` is what ``Trainer.eval_step`` returns: the loss when the batch carries labels, the model output otherwise; ``None`` on
   the ranks of a pipeline that do not hold the last stage — those batches are skipped); without it the mean loss is reported.
-  Ends with a barrier (reference ``_sync_signal``)."""
+
+  ``reduce`` (default): sums and batch counts are merged over all ranks, so every rank — also the first stage of a pipeline,
+  also each replica that evaluated its own shard of the data — returns the job-wide averages.  Either way the call ends with a
+  collective (the reference's ``_sync_signal`` barrier)."""
   sums: Dict[str, float] = {}
   n = 0
   for i, item in enumerate(data):
@@ -94,7 +97,17 @@ def evaluate(trainer, data: Iterable, metric_fn: Optional[Callable[[Any, Tuple[A
     for k, v in vals.items():
       sums[k] = sums.get(k, 0.0) + float(v)
     n += 1
-  _barrier()
+  import torch.distributed as dist
+  if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    parts: List[Any] = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, (sums, n))
+    sums, n = {}, 0
+    for part_sums, part_n in parts:
+      n += part_n
+      for k, v in part_sums.items():
+        sums[k] = sums.get(k, 0.0) + v
+  else:
+    _barrier()
   res = {k: v / max(n, 1) for k, v in sums.items()}
   res["batches"] = n
   return res

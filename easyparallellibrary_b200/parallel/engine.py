@@ -111,6 +111,12 @@ class Trainer(object):
       opt_kwargs = extra
       optimizer = optimizer.kind
     self.opt_kind = optimizer.lower()
+    # lr may be a schedule: a callable global_step -> learning rate (runtime/lr_schedule.py), evaluated before every step.  Every
+    # optimizer shard shares this one hyper-parameter object and reads lr per step (the CUDA-graph / fused paths through their
+    # device-side step values), so a schedule costs nothing and survives checkpoints (it is a function of global_step)
+    self.lr_schedule = opt_kwargs["lr"] if callable(opt_kwargs.get("lr")) else None
+    if self.lr_schedule is not None:
+      opt_kwargs = dict(opt_kwargs, lr=float(self.lr_schedule(0)))
     self.hyper = make_hyper(self.opt_kind, **opt_kwargs)
     self.max_grad_norm = max_grad_norm
     self.no_decay = no_decay
@@ -480,12 +486,23 @@ class Trainer(object):
         self._launched_buckets.add((s, b.index))
         self._launch_bucket_reduce(s, b)
 
+  @property
+  def lr(self) -> float:
+    """Learning rate of the next step (assign to change it; with a schedule the schedule wins)."""
+    return self.hyper.lr
+
+  @lr.setter
+  def lr(self, value: float) -> None:
+    self.hyper.lr = float(value)
+
   # ================================================================== one step
   def step(self, *batch, **kwargs) -> StepOutput:
     if not self._built:
       self.build()
     for h in self.hooks:
       h.before_step(self)
+    if self.lr_schedule is not None:
+      self.hyper.lr = float(self.lr_schedule(self.global_step))
     cfg = self.config
     mean = cfg.communication.gradients_reduce_method == constant.REDUCE_MEAN
     self._mean = mean

@@ -255,6 +255,7 @@ def main():
   ap.add_argument("--predict_batch_size", type=int, default=8)
   ap.add_argument("--learning_rate", type=float, default=3e-5)
   ap.add_argument("--num_train_steps", type=int, default=100)
+  ap.add_argument("--warmup_proportion", type=float, default=0.1, help="linear warm-up over this share of the steps, then linear decay to 0")
   ap.add_argument("--save_checkpoints_steps", type=int, default=0)
   ap.add_argument("--resume", action="store_true")
   ap.add_argument("--synthetic_paragraphs", type=int, default=60)
@@ -297,7 +298,9 @@ def main():
 
   model = Bert(bcfg)
   loss_fn = squad_loss if (args.num_pipe_stages > 1 or args.auto_parallel) else None
-  trainer = epl.Trainer(model, "adamw", lr=args.learning_rate, weight_decay=0.01, loss_fn=loss_fn).build()
+  from easyparallellibrary_b200.runtime.lr_schedule import warmup_linear_decay
+  schedule = warmup_linear_decay(args.learning_rate, args.num_train_steps, int(args.warmup_proportion * args.num_train_steps))
+  trainer = epl.Trainer(model, "adamw", lr=schedule, weight_decay=0.01, loss_fn=loss_fn).build()   # reference optimization.py:29-58
   if args.resume and os.path.exists(os.path.join(args.output_dir, "ckpt")):
     step0 = load_checkpoint(trainer, os.path.join(args.output_dir, "ckpt"))
     if rank == 0:

@@ -22,7 +22,8 @@ def _run(conf, steps=4, opt="adamw", **kw):
   epl.init(epl.Config(conf), init_process_group=False)
   with epl.replicate(1):
     model = _net()
-  tr = epl.Trainer(model, opt, loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2, **kw)
+  kw.setdefault("lr", 1e-2)
+  tr = epl.Trainer(model, opt, loss_fn=lambda o, y: ((o - y) ** 2).mean(), **kw)
   torch.manual_seed(1)
   X, Y = torch.randn(steps, 8, 8), torch.randn(steps, 8, 1)
   return [tr.step(X[i], Y[i]).item() for i in range(steps)], tr
@@ -435,3 +436,64 @@ def test_train_evaluate_loops_and_resume(tmp_path):
   # evaluate with a metric function on the model output (no labels in the batch)
   acc = epl.evaluate(b, [x for x, _ in evald], metric_fn=lambda out, batch: {"mean_abs": out.abs().mean()})
   assert acc["batches"] == 2 and acc["mean_abs"] > 0
+
+
+def test_learning_rate_schedules():
+  """``Trainer(lr=schedule)``: the schedule is evaluated per global step, equals setting ``trainer.lr`` by hand, and resumes with
+  the checkpointed step (reference: tf.train.exponential_decay in tests/multi_optimizer_test.py:59-62, BERT warm-up + decay)."""
+  from easyparallellibrary_b200.runtime import lr_schedule as L
+  s = L.warmup_linear_decay(1e-3, total_steps=10, warmup_steps=4)
+  assert [round(s(i) / 1e-3, 4) for i in (0, 3, 4, 9, 10, 50)] == [0.25, 0.7, 0.6, 0.1, 0.0, 0.0]
+  e = L.exponential_decay(0.1, 5, 0.96)
+  assert abs(e(5) - 0.096) < 1e-12 and abs(L.exponential_decay(0.1, 5, 0.96, staircase=True)(9) - 0.096) < 1e-12
+  c = L.warmup_cosine(1.0, 100, 10, 0.1)
+  assert abs(c(9) - 1.0) < 1e-9 and abs(c(100) - 0.1) < 1e-9 and abs(c(55) - 0.55) < 1e-9 and c(4) == 0.5
+  sched = L.warmup(L.exponential_decay(2e-2, 3, 0.5), 2)
+  auto, tr = _run({}, steps=5, lr=sched)
+  assert tr.lr_schedule is sched and abs(tr.lr - sched(4)) < 1e-12
+  # the same learning rates assigned by hand
+  epl.init(epl.Config({}), init_process_group=False)
+  with epl.replicate(1):
+    model = _net()
+  tr2 = epl.Trainer(model, "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=123.0)
+  torch.manual_seed(1)
+  X, Y = torch.randn(5, 8, 8), torch.randn(5, 8, 1)
+  manual = []
+  for i in range(5):
+    tr2.lr = sched(i)
+    manual.append(tr2.step(X[i], Y[i]).item())
+  assert max(abs(a - b) for a, b in zip(auto, manual)) < 1e-7
+  const, _ = _run({}, steps=5, lr=2e-2)
+  assert max(abs(a - b) for a, b in zip(auto[2:], const[2:])) > 1e-6          # the schedule does change the trajectory
+
+
+def test_weight_ema_hook_with_clipping():
+  """The reference's nested optimizer (Adam -> clip_gradients_by_norm -> MovingAverageOptimizer, tests/multi_optimizer_test.py:30-36)
+  as ``max_grad_norm`` + a ``WeightEMA`` hook: the shadow weights follow TF's formula and can be swapped in for evaluation."""
+  from easyparallellibrary_b200.runtime.ema import WeightEMA
+  epl.init(epl.Config({"communication.clip_after_allreduce": True}), init_process_group=False)
+  with epl.replicate(1):
+    model = _net()
+  tr = epl.Trainer(model, "adam", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2, max_grad_norm=0.5)
+  ema = WeightEMA(decay=0.1, num_updates=True)
+  tr.hooks.append(ema)
+  torch.manual_seed(1)
+  X, Y = torch.randn(4, 8, 8), torch.randn(4, 8, 1)
+  p0 = next(model.parameters())
+  expect = p0.detach().clone()
+  for i in range(4):
+    out = tr.step(X[i], Y[i])
+    assert out.grad_norm is not None
+    d = min(0.1, (1.0 + i) / (10.0 + i))
+    expect = d * expect + (1 - d) * p0.detach()
+  name = ema._names[0]
+  assert torch.allclose(ema.shadow[name], expect, atol=1e-7) and ema.updates == 4
+  trained = p0.detach().clone()
+  plain = tr.eval_step(X[0], Y[0]).item()
+  with ema.swapped(tr):
+    assert torch.allclose(p0, expect, atol=1e-7)
+    averaged = tr.eval_step(X[0], Y[0]).item()
+  assert torch.equal(p0.detach(), trained) and averaged != plain
+  other = WeightEMA(decay=0.1, num_updates=True)
+  other.load_state_dict(ema.state_dict())
+  assert other.updates == 4 and torch.equal(other.shadow[name], ema.shadow[name])

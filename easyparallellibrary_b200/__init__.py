@@ -105,6 +105,9 @@ def __getattr__(name):
   if name == "prepare":
     from easyparallellibrary_b200.parallel.engine import prepare
     return prepare
+  if name == "summary":
+    from easyparallellibrary_b200.utils import summary
+    return summary
   if name in ("train", "evaluate", "train_and_evaluate"):
     from easyparallellibrary_b200.runtime import loop
     return getattr(loop, name)

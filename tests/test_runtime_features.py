@@ -497,3 +497,42 @@ def test_weight_ema_hook_with_clipping():
   other = WeightEMA(decay=0.1, num_updates=True)
   other.load_state_dict(ema.state_dict())
   assert other.updates == 4 and torch.equal(other.shadow[name], ema.shadow[name])
+
+
+def test_named_summaries_are_merged_and_written(tmp_path):
+  """``epl.summary.scalar / histogram`` inside the model (reference: tf.summary under EPL, tests/summary_test.py:31-110): merged over
+  the micro-batches like their collection, described in ``Graph.summary_map``, written by ``SummaryHook``."""
+  import json as _json
+
+  class Net(nn.Module):
+    def __init__(self):
+      super().__init__()
+      self.fc = nn.Linear(8, 4)
+
+    def forward(self, x, labels):
+      logits = self.fc(x)
+      epl.summary.histogram("features", x)
+      epl.summary.scalar("mean_acc", (logits.argmax(-1) == labels).float().mean())
+      epl.summary.scalar("rows", torch.tensor(float(x.shape[0])), reduce="sum")
+      return nn.functional.cross_entropy(logits, labels)
+
+  epl.init(epl.Config({"pipeline.num_micro_batch": 2}), init_process_group=False)
+  with epl.replicate(1):
+    model = Net()
+  tr = epl.Trainer(model, "sgd", lr=0.1)
+  hook = epl.summary.SummaryHook(str(tmp_path), every=2)
+  tr.hooks.append(hook)
+  torch.manual_seed(0)
+  x, y = torch.randn(6, 8), torch.randint(0, 4, (6,))
+  outs = [tr.step(x, y) for _ in range(4)]
+  hook.close()
+  smap = epl.Graph.get().summary_map
+  assert sorted(smap) == ["features", "mean_acc", "rows"]
+  assert smap["features"].summary_type == "SUMMARY_HISTOGRAM_TYPE" and smap["features"].collection == epl.GraphKeys.GLOBAL_CONCAT_OBJECTS
+  assert smap["mean_acc"].summary_type == "SUMMARY_SCALAR_TYPE" and smap["rows"].collection == epl.GraphKeys.GLOBAL_SUM_OBJECTS
+  merged = epl.summary.merged_summaries(outs[-1])
+  assert merged["features"].shape == (6, 8) and float(merged["rows"]) == 6.0 and 0.0 <= float(merged["mean_acc"]) <= 1.0
+  rows = [_json.loads(l) for l in open(os.path.join(tmp_path, "summaries.jsonl"))]
+  assert [r["step"] for r in rows] == [2, 4] and rows[0]["rows"] == 6.0 and rows[0]["features"]["count"] == 48
+  assert all(k in rows[1] for k in ("loss", "lr", "loss_scale", "mean_acc"))
+  assert any(f.startswith("events.out.tfevents") for f in os.listdir(tmp_path))      # TensorBoard events next to the JSON lines

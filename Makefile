@@ -14,6 +14,7 @@ test-gpu:         ## kernel numerics + multi-GPU parity (needs a B200)
 
 lint:             ## syntax / import check of the package, -Wall build of the host runtime
 	$(PY) -m compileall -q easyparallellibrary_b200 tests examples tools bench.py
+	$(PY) tools/check_globals.py          # every global name and every ctypes symbol resolves (GPU-only branches included)
 	g++ -O2 -std=c++17 -fPIC -Wall -Werror=return-type -fsyntax-only -I/usr/local/cuda/include easyparallellibrary_b200/csrc/runtime.cpp
 
 sanitize:         ## memory / race / sync checks of the kernels (needs a B200; slow: kernels run ~50x slower)

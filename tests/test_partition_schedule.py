@@ -150,3 +150,27 @@ def test_scoped_models_split_their_blocks_evenly(family):
   first = round((n_blocks + 50257 / (12.0 * 768)) / 2) if family == "gpt2" else n_blocks // 2
   assert assign.count(0) == 1 + first and assign.count(1) == 1 + n_blocks - first, assign
   epl.shutdown()
+
+
+def test_stage_function_reads_the_loss_scale_from_a_tensor():
+  """``parallel/pipeline.py::_StageFn`` (what a captured stage graph runs): loss scale x 1/M is a device scalar, so a dynamic loss
+  scale changes the replayed program's result without re-capturing."""
+  import torch
+  from torch import nn
+  from easyparallellibrary_b200.parallel.pipeline import _StageFn
+  torch.manual_seed(0)
+  lin = nn.Linear(4, 1)
+  fn = _StageFn(lin, lambda y, t: ((y - t) ** 2).mean(), 8.0, device="cpu")
+  x, t = torch.randn(3, 4), torch.randn(3, 1)
+  plain = ((lin(x) - t) ** 2).mean()
+  y = fn(x, t)
+  assert torch.allclose(y, plain * 8.0)
+  (g8,) = torch.autograd.grad(y, lin.weight)
+  fn.set_factor(2.0)
+  assert fn.factor == 2.0 and float(fn.factor_t) == 2.0
+  y2 = fn(x, t)
+  (g2,) = torch.autograd.grad(y2, lin.weight)
+  assert torch.allclose(y2, plain * 2.0) and torch.allclose(g8, g2 * 4.0)
+  assert list(p for p in fn.parameters()) == list(lin.parameters())           # the scalar is not a parameter of the stage
+  mid = _StageFn(lin, None, 1.0)                                               # a stage without the loss passes its output through
+  assert mid.factor_t is None and torch.equal(mid(x), lin(x))

@@ -104,6 +104,12 @@ class Trainer(object):
     self.config = env.config
     self.model = model
     self.loss_fn = loss_fn
+    if isinstance(optimizer, type) and issubclass(optimizer, torch.optim.Optimizer):
+      # any torch optimizer class (Adagrad, RMSprop, ...): runs on the fp32 master shards through the library path, so ZeRO
+      # sharding, gradient accumulation, clipping, loss scaling and checkpoints keep working; the fused kernels and the
+      # CUDA-graph step need one of the built-in optimizers
+      opt_kwargs = dict(opt_kwargs, factory=optimizer)
+      optimizer = "torch"
     if not isinstance(optimizer, str):          # an optimizer description object (e.g. ops.AdamWeightDecayOptimizer)
       extra = optimizer.trainer_kwargs(model)
       no_decay = extra.pop("no_decay", no_decay)
@@ -138,6 +144,9 @@ class Trainer(object):
     cfg, env = self.config, self.env
     graph = Graph.get()
     self.device = self._device or local_device()
+    if self.opt_kind == "torch" and cfg.offload.level:
+      raise ValueError("offload.level=%s streams the optimizer state through a device window for the built-in optimizers "
+                       "(adam | adamw | sgd); a torch.optim class keeps its own state tensors" % cfg.offload.level)
     if cfg.auto.auto_parallel and cfg.pipeline.num_stages > 1:
       self._auto_stages(graph)
     self.plan: ParallelPlan = build_plan(graph, env.cluster, cfg)
@@ -813,6 +822,9 @@ class Trainer(object):
 
   def _baseline_apply(self, opt: FlatOptimizer, g, p, scale) -> None:
     from easyparallellibrary_b200.runtime.optimizer import adamw_reference, sgd_reference
+    if opt.kind == "torch":
+      opt.step(g, p, scale)
+      return
     opt.step_count += 1
     out = p if p.data_ptr() != opt.master.data_ptr() else None
     if opt.kind == "sgd":

@@ -40,6 +40,15 @@ class SGDHyper:
   weight_decay: float = 0.0
 
 
+@dataclass
+class TorchHyper:
+  """Any ``torch.optim.Optimizer`` class, applied to the fp32 master shards (library speed: no fused kernel, no CUDA graph)."""
+  lr: float = 1e-3
+  weight_decay: float = 0.0
+  factory: Optional[type] = None
+  kwargs: Optional[dict] = None
+
+
 def adamw_reference(master: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int,
                     h: AdamHyper, grad_scale: float = 1.0, decay_mask: Optional[torch.Tensor] = None,
                     model_out: Optional[torch.Tensor] = None) -> None:
@@ -94,8 +103,36 @@ class FlatOptimizer(object):
     elif self.kind == "sgd":
       self.m = torch.zeros_like(master_shard, device=dev) if hyper.momentum else None
       self.v = None
+    elif self.kind == "torch":
+      # a wrapped torch optimizer sees the shard as a few fp32 parameters: one per run of equal weight-decay mask values (the
+      # mask is constant over each model parameter, and model parameters are contiguous ranges of the flat buffer), in two groups
+      self.m = self.v = None
+      self._segments = []                          # (lo, hi, nn.Parameter viewing master[lo:hi])
+      groups = {True: [], False: []}
+      n = master_shard.numel()
+      if decay_mask is None or n == 0:
+        bounds = [0, n]
+        decays = [True]
+      else:
+        change = (torch.nonzero(decay_mask[1:] != decay_mask[:-1]).flatten() + 1).tolist()
+        bounds = [0] + change + [n]
+        decays = [bool(decay_mask[b] != 0) for b in bounds[:-1]]
+      for (a, b), d in zip(zip(bounds[:-1], bounds[1:]), decays):
+        if b > a:
+          p = torch.nn.Parameter(master_shard[a:b], requires_grad=True)      # shares the master's storage: updated in place
+          self._segments.append((a, b, p))
+          groups[d].append(p)
+      kw = dict(hyper.kwargs or {})
+      param_groups = []
+      if groups[True]:
+        param_groups.append({"params": groups[True]})
+      if groups[False]:
+        param_groups.append(dict({"params": groups[False]}, **({"weight_decay": 0.0} if "weight_decay" in kw or hyper.weight_decay else {})))
+      if hyper.weight_decay:
+        kw["weight_decay"] = hyper.weight_decay
+      self.opt = hyper.factory(param_groups or [{"params": [torch.nn.Parameter(master_shard[:0])]}], lr=hyper.lr, **kw)
     else:
-      raise ValueError("unknown optimizer %r (adam | adamw | sgd)" % kind)
+      raise ValueError("unknown optimizer %r (adam | adamw | sgd | a torch.optim.Optimizer class)" % kind)
     self.step_count = 0
     self.dyn: Optional[torch.Tensor] = None        # device {lr, inv_c1, inv_c2, grad scale}: set by the engine in CUDA-graph mode
 
@@ -110,6 +147,22 @@ class FlatOptimizer(object):
     sl = slice(lo, hi)
     out = model_shard[sl] if model_shard is not None and model_shard.data_ptr() != self.master.data_ptr() else None
     mask = self.decay_mask[sl] if self.decay_mask is not None else None
+    if self.kind == "torch":
+      if lo != 0 or hi != self.master.numel():
+        raise NotImplementedError("optimizer.num_apply_group > 1 needs one of the built-in optimizers (adam | adamw | sgd)")
+      g = grad_shard.to(torch.float32)
+      if grad_scale != 1.0:
+        g = g * grad_scale
+      for a, b, p in self._segments:
+        p.grad = g[a:b]
+      for group in self.opt.param_groups:
+        group["lr"] = self.hyper.lr                 # schedules / trainer.lr act on the shared hyper object
+      self.opt.step()
+      for _, _, p in self._segments:
+        p.grad = None
+      if out is not None:
+        out.copy_(self.master[sl])
+      return
     if self.master.is_cuda:
       from easyparallellibrary_b200.ops import fused_optim
       if self.kind == "sgd":
@@ -126,11 +179,26 @@ class FlatOptimizer(object):
                       grad_scale, mask, out)
 
   def state_dict(self):
-    return {"kind": self.kind, "step": self.step_count, "m": self.m, "v": self.v, "master": self.master}
+    sd = {"kind": self.kind, "step": self.step_count, "m": self.m, "v": self.v, "master": self.master}
+    if self.kind == "torch":
+      # flat "t<param index>.<state name>" entries (tensors / numbers) so the sharded saver can store them like m / v
+      for idx, st in self.opt.state_dict()["state"].items():
+        for name, val in st.items():
+          sd["t%d.%s" % (idx, name)] = val
+    return sd
 
   def load_state_dict(self, sd) -> None:
     self.step_count = int(sd["step"])
     self.master.copy_(sd["master"])
+    if self.kind == "torch":
+      state = {}
+      for k, v in sd.items():
+        if k[:1] == "t" and "." in k and k[1:k.index(".")].isdigit():
+          state.setdefault(int(k[1:k.index(".")]), {})[k[k.index(".") + 1:]] = v
+      if state:
+        osd = self.opt.state_dict()
+        osd["state"] = state
+        self.opt.load_state_dict(osd)
     if self.m is not None and sd.get("m") is not None:
       self.m.copy_(sd["m"])
     if self.v is not None and sd.get("v") is not None:
@@ -139,6 +207,10 @@ class FlatOptimizer(object):
 
 def make_hyper(kind: str, **kw):
   kind = kind.lower()
+  if kind == "torch":
+    kw = dict(kw)
+    factory = kw.pop("factory")
+    return TorchHyper(lr=kw.pop("lr", 1e-3), weight_decay=kw.pop("weight_decay", 0.0), factory=factory, kwargs=kw)
   if kind == "sgd":
     return SGDHyper(lr=kw.get("lr", 1e-2), momentum=kw.get("momentum", 0.0), weight_decay=kw.get("weight_decay", 0.0))
   betas = kw.get("betas", (kw.get("beta1", 0.9), kw.get("beta2", 0.999)))

@@ -209,8 +209,9 @@ def load_checkpoint(trainer, directory: str) -> int:
       for i, o in enumerate(trainer.optimizers[s]):
         pre = "g%d.b%d." % (s, i)
         if pre + "master" in opt and opt[pre + "master"].numel() == o.master.numel():
-          o.load_state_dict({"step": int(opt[pre + "step"]), "master": opt[pre + "master"],
-                             "m": opt.get(pre + "m"), "v": opt.get(pre + "v")})
+          sd = {"step": int(opt[pre + "step"]), "master": opt[pre + "master"], "m": opt.get(pre + "m"), "v": opt.get(pre + "v")}
+          sd.update({k[len(pre):]: v for k, v in opt.items() if k.startswith(pre + "t")})      # wrapped torch optimizers: "t<i>.<name>"
+          o.load_state_dict(sd)
           restored.add((s, i))
     for s, z in zero3.items():
       sds = []

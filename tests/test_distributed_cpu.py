@@ -117,6 +117,16 @@ def test_data_parallel_matches_single_process(conf):
   assert _max_diff(dist_res[0][1], dist_res[1][1]) == 0.0       # replicas stay bit-identical
 
 
+@pytest.mark.parametrize("conf", [{}, {"zero.level": "v1"}])
+def test_wrapped_torch_optimizer_under_data_parallel(conf):
+  """A torch optimizer class (here Adagrad) on the fp32 master shards: two ranks (optionally ZeRO-1 shards) == one process."""
+  base = run_distributed(_train, 1, args=({}, 4, None, torch.optim.Adagrad))[0]
+  two = run_distributed(_train, 2, args=(conf, 4, None, torch.optim.Adagrad))
+  for res in two:
+    assert _max_diff(base[1], res[1]) < 1e-6
+  assert _max_diff(two[0][1], two[1][1]) == 0.0
+
+
 def test_sgd_and_clipping_modes():
   for conf in ({}, {"communication.clip_after_allreduce": True}):
     base = run_distributed(_train, 1, args=({}, 3, 0.5, "sgd"))[0]

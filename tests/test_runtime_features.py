@@ -536,3 +536,49 @@ def test_named_summaries_are_merged_and_written(tmp_path):
   assert [r["step"] for r in rows] == [2, 4] and rows[0]["rows"] == 6.0 and rows[0]["features"]["count"] == 48
   assert all(k in rows[1] for k in ("loss", "lr", "loss_scale", "mean_acc"))
   assert any(f.startswith("events.out.tfevents") for f in os.listdir(tmp_path))      # TensorBoard events next to the JSON lines
+
+
+@pytest.mark.parametrize("cls,kw", [(torch.optim.Adagrad, {}), (torch.optim.RMSprop, {"momentum": 0.5}), (torch.optim.Adam, {"amsgrad": True})])
+def test_any_torch_optimizer_class(cls, kw, tmp_path):
+  """``Trainer(model, torch.optim.X, ...)``: the reference accepts whatever TF optimizer the model uses; here any torch optimizer
+  class runs on the fp32 master shards and must match the same optimizer on a plain model — also with ZeRO-1, gradient
+  accumulation, a learning-rate schedule, no-decay parameters and a checkpoint round trip."""
+  from easyparallellibrary_b200.runtime import lr_schedule as L, saver
+  sched = L.exponential_decay(1e-2, 2, 0.5)
+  torch.manual_seed(0)
+  ref_model = _net()
+  decay = [p for p in ref_model.parameters() if p.dim() > 1]
+  nodecay = [p for p in ref_model.parameters() if p.dim() <= 1]
+  ref_opt = cls([{"params": decay, "weight_decay": 0.1}, {"params": nodecay, "weight_decay": 0.0}], lr=1e-2, **kw)
+  torch.manual_seed(1)
+  X, Y = torch.randn(5, 8, 8), torch.randn(5, 8, 1)
+  ref = []
+  for i in range(5):
+    for g in ref_opt.param_groups:
+      g["lr"] = sched(i)
+    ref_opt.zero_grad()
+    loss = ((ref_model(X[i]) - Y[i]) ** 2).mean()
+    loss.backward()
+    ref_opt.step()
+    ref.append(loss.item())
+
+  def make(conf):
+    epl.init(epl.Config(conf), init_process_group=False)
+    torch.manual_seed(0)
+    with epl.replicate(1):
+      model = _net()
+    return epl.Trainer(model, cls, loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=sched, weight_decay=0.1, **kw)
+
+  for conf in ({}, {"zero.level": "v1"}, {"pipeline.num_micro_batch": 2}):
+    tr = make(conf)
+    got = [tr.step(X[i], Y[i]).item() for i in range(5)]
+    assert max(abs(a - b) for a, b in zip(got, ref)) < 2e-6, (conf, got, ref)
+  a = make({})
+  for i in range(3):
+    a.step(X[i], Y[i])
+  saver.save_checkpoint(a, str(tmp_path))
+  b = make({})
+  assert saver.load_checkpoint(b, str(tmp_path)) == 3
+  assert abs(b.step(X[3], Y[3]).item() - ref[3]) < 2e-6 and abs(b.step(X[4], Y[4]).item() - ref[4]) < 2e-6
+  with pytest.raises(ValueError):
+    make({"offload.level": "v0"}).build()

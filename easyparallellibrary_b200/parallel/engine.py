@@ -104,6 +104,27 @@ class Trainer(object):
     self.config = env.config
     self.model = model
     self.loss_fn = loss_fn
+    if isinstance(optimizer, torch.optim.Optimizer):
+      # an optimizer INSTANCE built over model.parameters() the usual PyTorch way: its class and defaults are taken over (the
+      # instance itself is not used: the engine owns flat fp32 master shards).  Per-group settings other than weight decay are
+      # not carried; parameters of groups with weight_decay == 0 join the no-decay set.
+      inst = optimizer
+      defaults = {k: v for k, v in inst.defaults.items() if k not in ("params",)}
+      if len({g.get("lr", defaults.get("lr")) for g in inst.param_groups}) > 1:
+        get_logger().warning("Trainer: the optimizer's param groups use different learning rates; only the default (%s) is used",
+                             defaults.get("lr"))
+      wds = [g.get("weight_decay", defaults.get("weight_decay", 0.0)) for g in inst.param_groups]
+      zero_wd = {id(p) for g, w in zip(inst.param_groups, wds) if not w for p in g["params"]}
+      if any(wds):
+        defaults["weight_decay"] = max(wds)
+      if no_decay is default_no_decay:             # follow the instance exactly: torch decays biases too unless a group says otherwise
+        no_decay = lambda p, _z=zero_wd: id(p) in _z                           # noqa: E731
+      else:
+        user_nd = no_decay
+        no_decay = lambda p, _u=user_nd, _z=zero_wd: id(p) in _z or _u(p)      # noqa: E731
+      defaults.update(opt_kwargs)
+      opt_kwargs = defaults
+      optimizer = type(inst)
     if isinstance(optimizer, type) and issubclass(optimizer, torch.optim.Optimizer):
       # any torch optimizer class (Adagrad, RMSprop, ...): runs on the fp32 master shards through the library path, so ZeRO
       # sharding, gradient accumulation, clipping, loss scaling and checkpoints keep working; the fused kernels and the

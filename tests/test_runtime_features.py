@@ -582,3 +582,40 @@ def test_any_torch_optimizer_class(cls, kw, tmp_path):
   assert abs(b.step(X[3], Y[3]).item() - ref[3]) < 2e-6 and abs(b.step(X[4], Y[4]).item() - ref[4]) < 2e-6
   with pytest.raises(ValueError):
     make({"offload.level": "v0"}).build()
+
+
+def test_torch_optimizer_instance_is_taken_over():
+  """``Trainer(model, torch.optim.X(model.parameters(), ...))``: class, defaults and the groups' weight-decay split are taken over."""
+  torch.manual_seed(0)
+  ref_model = _net()
+  ref_opt = torch.optim.RMSprop(ref_model.parameters(), lr=3e-3, alpha=0.9, weight_decay=0.05)      # decays biases too
+  torch.manual_seed(1)
+  X, Y = torch.randn(4, 8, 8), torch.randn(4, 8, 1)
+  ref = []
+  for i in range(4):
+    ref_opt.zero_grad()
+    loss = ((ref_model(X[i]) - Y[i]) ** 2).mean()
+    loss.backward()
+    ref_opt.step()
+    ref.append(loss.item())
+  epl.init(epl.Config({}), init_process_group=False)
+  torch.manual_seed(0)
+  with epl.replicate(1):
+    model = _net()
+  decay = [p for p in model.parameters() if p.dim() > 1]
+  inst = torch.optim.RMSprop(model.parameters(), lr=3e-3, alpha=0.9, weight_decay=0.05)
+  tr = epl.Trainer(model, inst, loss_fn=lambda o, y: ((o - y) ** 2).mean())
+  assert tr.opt_kind == "torch" and tr.hyper.factory is torch.optim.RMSprop and tr.hyper.kwargs["alpha"] == 0.9 and tr.lr == 3e-3
+  got = [tr.step(X[i], Y[i]).item() for i in range(4)]
+  assert max(abs(a - b) for a, b in zip(got, ref)) < 2e-6
+  # two groups: the zero-weight-decay group becomes the no-decay set
+  epl.init(epl.Config({}), init_process_group=False)
+  torch.manual_seed(0)
+  with epl.replicate(1):
+    model = _net()
+  decay = [p for p in model.parameters() if p.dim() > 1]
+  rest = [p for p in model.parameters() if p.dim() <= 1]
+  inst = torch.optim.SGD([{"params": decay, "weight_decay": 0.1}, {"params": rest, "weight_decay": 0.0}], lr=1e-2, momentum=0.9)
+  tr = epl.Trainer(model, inst, loss_fn=lambda o, y: ((o - y) ** 2).mean())
+  assert tr.hyper.weight_decay == 0.1 and all(tr.no_decay(p) for p in rest) and not any(tr.no_decay(p) for p in decay)
+  tr.step(X[0], Y[0])

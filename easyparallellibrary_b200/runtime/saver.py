@@ -178,6 +178,59 @@ def save_checkpoint(trainer, directory: str, bucket_bytes: int = BUCKET_BYTES) -
   return files
 
 
+def _reshard_optimizer_state(trainer, directory: str, restored: set) -> None:
+  """Elastic resume: the checkpoint was written with another data-parallel degree (or without sharding), so no file holds this
+  rank's shard.  A flat bucket's optimizer state is the concatenation of the old ranks' shards in rank order — the parameters sit
+  at the same (world-independent) offsets, only the tail padding differs — so it is rebuilt from every ``rank<r>/optim`` (or the
+  unsharded ``optim``) and re-sliced for the new layout.  The reference cannot do this (its ZeRO shards are never merged,
+  ``hooks.py:546-547``).  Pipelines, split taskgraphs and ZeRO-3 units keep the restart-from-weights fallback."""
+  todo = [(s, i) for s in trainer.group_keys for i in range(len(trainer.optimizers[s])) if (s, i) not in restored]
+  if not todo or trainer.plan.num_stages > 1 or getattr(trainer, "has_split", False) or getattr(trainer, "zero3", {}):
+    return
+  parts = []
+  if os.path.exists(os.path.join(directory, "optim.index.json")):
+    parts = [MemoryEfficientBuilder(directory).load("optim")[0]]            # written unsharded: one full copy
+  else:
+    ranks = sorted(int(d[4:]) for d in os.listdir(directory) if d.startswith("rank") and d[4:].isdigit()
+                   and os.path.exists(os.path.join(directory, d, "optim.index.json")))
+    if ranks != list(range(len(ranks))):
+      return                                                                  # a rank directory is missing: cannot rebuild
+    parts = [MemoryEfficientBuilder(os.path.join(directory, "rank%d" % r)).load("optim")[0] for r in ranks]
+  if not parts:
+    return
+  from easyparallellibrary_b200.utils.logging import get_logger
+  for s, i in todo:
+    b, o = trainer.flats[s].buckets[i], trainer.optimizers[s][i]
+    pre = "g%d.b%d." % (s, i)
+    if o.kind == "torch" or not all(pre + "master" in part for part in parts):
+      continue
+    used = max((off + p.numel() for p, off in zip(b.params, b.offsets)), default=0)
+    comm, sharded = trainer.dp_comms[s], trainer._sharded[s]
+    lo, hi = b.shard_range(comm.rank if sharded else 0, comm.size if sharded else 1)
+    sd = {"step": int(parts[0][pre + "step"])}
+    ok = True
+    for k in ("master", "m", "v"):
+      if getattr(o, k, None) is None:
+        sd[k] = None
+        continue
+      if not all(part.get(pre + k) is not None for part in parts):
+        ok = False
+        break
+      full = torch.cat([part[pre + k].reshape(-1) for part in parts])
+      if full.numel() < used:
+        ok = False
+        break
+      piece = torch.zeros(hi - lo, dtype=full.dtype)
+      n = max(min(hi, full.numel()) - lo, 0)
+      if n:
+        piece[:n] = full[lo:lo + n]
+      sd[k] = piece
+    if ok:
+      o.load_state_dict(sd)
+      restored.add((s, i))
+      get_logger().info("optimizer state of bucket %d.%d re-sliced from %d checkpoint shard(s)", s, i, len(parts))
+
+
 def load_checkpoint(trainer, directory: str) -> int:
   """Restore on every rank from the files written by ``save_checkpoint``; returns the restored global step."""
   trainer.build()
@@ -243,6 +296,7 @@ def load_checkpoint(trainer, directory: str) -> int:
         (u.shard_host if u.offload else u.shard_param).copy_(shard)
         u.opt.master.copy_(shard.to(u.opt.master.dtype))           # moments restart at zero: the optimizer state was not in the checkpoint
       restored.add(("zero3", s))
+  _reshard_optimizer_state(trainer, directory, restored)
   # optimizers without restored state restart from the restored weights (fp32 master = parameters)
   for s in trainer.group_keys:
     comm, flat = trainer.dp_comms[s], trainer.flats[s]

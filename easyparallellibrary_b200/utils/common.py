@@ -45,3 +45,28 @@ def gcd_many(values: Iterable[int]) -> int:
 
 def lcm_many(values: Iterable[int]) -> int:
   return reduce(lambda a, b: a * b // math.gcd(a, b) if a and b else 0, values, 1)
+
+
+def fix_randomness(seed: int = 0, deterministic: bool = True) -> None:
+  """Seed every generator and ask the libraries for deterministic algorithms — what the reference's A/B tests do before comparing
+  two runs to 1e-5 / 1e-6 (``tests/test_utils.py:25-33``: seeds + ``TF_DETERMINISTIC_OPS``).  Call it before building the model.
+
+  The in-tree kernels are deterministic for a fixed launch configuration except where partial results meet in memory in arrival
+  order: the dQ accumulation of the attention backward (TMA reduce-add over key tiles) and bf16 weight-gradient accumulation
+  across micro-batches; runs then agree to rounding, not bit for bit."""
+  import os
+  import random
+  import numpy as np
+  import torch
+  random.seed(seed)
+  np.random.seed(seed % (2 ** 32))
+  torch.manual_seed(seed)
+  if torch.cuda.is_available():
+    torch.cuda.manual_seed_all(seed)
+  if deterministic:
+    os.environ.setdefault("CUBLAS_WORKSPACE_CONFIG", ":4096:8")
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.use_deterministic_algorithms(True, warn_only=True)
+  else:
+    torch.use_deterministic_algorithms(False)

@@ -619,3 +619,20 @@ def test_torch_optimizer_instance_is_taken_over():
   tr = epl.Trainer(model, inst, loss_fn=lambda o, y: ((o - y) ** 2).mean())
   assert tr.hyper.weight_decay == 0.1 and all(tr.no_decay(p) for p in rest) and not any(tr.no_decay(p) for p in decay)
   tr.step(X[0], Y[0])
+
+
+def test_fix_randomness_makes_runs_repeatable():
+  from easyparallellibrary_b200.utils.common import fix_randomness
+
+  def run():
+    fix_randomness(7)
+    epl.init(epl.Config({}), init_process_group=False)
+    with epl.replicate(1):
+      model = nn.Sequential(nn.Linear(8, 16), nn.Dropout(0.5), nn.Linear(16, 1))      # unseeded init AND dropout
+    tr = epl.Trainer(model, "adamw", loss_fn=lambda o, y: ((o - y) ** 2).mean(), lr=1e-2)
+    return [tr.step(torch.randn(4, 8), torch.randn(4, 1)).item() for _ in range(3)]
+
+  try:
+    assert run() == run()
+  finally:
+    fix_randomness(0, deterministic=False)
